@@ -1,0 +1,334 @@
+// la_api.cu -- the C ABI (include/lyricalign.h): plans, workspace layout, kernel dispatch.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lyricalign.h"
+#include "la_common.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return LA_ERR_CUDA;
+}
+#define LA_CUDA(x)                                            \
+    do {                                                      \
+        cudaError_t e__ = (x);                                \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #x);    \
+    } while (0)
+
+constexpr int kBuckets = 5;
+
+struct la_plan {
+    int mode = 0, n_utt = 0, V = 0, device = 0, sm_count = 148;
+    int64_t total_T = 0, total_L = 0;
+    std::vector<int32_t> t_off, l_off, e_row, bp_pairs;
+    std::vector<int64_t> e_off, bp_off;     // floats / uint32 words, relative to their area
+    size_t emit_bytes = 0, bp_bytes = 0;
+    std::vector<int32_t> order[kBuckets];
+    int row_max[kBuckets] = {0, 0, 0, 0, 0};
+    int wide_warps[kBuckets] = {0, 0, 0, 0, 0};
+    // device metadata blob
+    void* d_meta = nullptr;
+    la::BatchMeta meta{};
+    const int32_t* d_order[kBuckets] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // host-path staging (la_align_host)
+    void* d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    void* d_ws = nullptr;
+    void* d_out = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" {
+
+const char* la_version(void) { return "lyricalign-b200 0.1 (sm_100a)"; }
+const char* la_last_error(void) { return g_err.c_str(); }
+int la_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int la_plan_create(la_plan** out, int mode, int n_utt, int V, const int32_t* h_t_len,
+                   const int32_t* h_l_len, const int32_t* h_labels, int device) {
+    if (!out || n_utt < 0 || (n_utt > 0 && (!h_t_len || !h_l_len))) return fail(LA_ERR_ARG, "null argument");
+    if (mode < 0 || mode > 2) return fail(LA_ERR_ARG, "mode must be LA_MODE_CTC/CE/LOGP");
+    if ((mode == LA_MODE_CTC && V < 3) || V < 1) return fail(LA_ERR_ARG, "V too small for this mode");
+    la_plan* P = new (std::nothrow) la_plan();
+    if (!P) return fail(LA_ERR_ALLOC, "out of host memory");
+    P->mode = mode; P->n_utt = n_utt; P->V = V; P->device = device;
+    P->t_off.assign(n_utt + 1, 0);
+    P->l_off.assign(n_utt + 1, 0);
+    P->e_row.assign(n_utt, 0);
+    P->bp_pairs.assign(n_utt, 0);
+    P->e_off.assign(n_utt, 0);
+    P->bp_off.assign(n_utt, 0);
+    int64_t tsum = 0, lsum = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        if (h_t_len[u] < 0 || h_l_len[u] < 0) { delete P; return fail(LA_ERR_ARG, "negative length"); }
+        if (h_l_len[u] > LA_MAX_LABELS) { delete P; return fail(LA_ERR_LIMIT, "label row longer than LA_MAX_LABELS"); }
+        tsum += h_t_len[u]; lsum += h_l_len[u];
+        if (tsum > INT32_MAX || lsum > INT32_MAX) { delete P; return fail(LA_ERR_LIMIT, "batch too large for int32 offsets"); }
+        P->t_off[u + 1] = (int32_t)tsum;
+        P->l_off[u + 1] = (int32_t)lsum;
+    }
+    P->total_T = tsum; P->total_L = lsum;
+    if (lsum > 0 && !h_labels) { delete P; return fail(LA_ERR_ARG, "null labels"); }
+    for (int64_t i = 0; i < lsum; ++i)
+        if (h_labels[i] < 0 || h_labels[i] >= V) { delete P; return fail(LA_ERR_ARG, "label column out of range"); }
+
+    // buckets + workspace layout
+    int wide_need[kBuckets] = {0, 0, 0, 0, 0};
+    std::vector<int> bucket_of(n_utt, 0);
+    for (int u = 0; u < n_utt; ++u) {
+        const int L = h_l_len[u], pairs = L + 1;
+        int b;
+        if (pairs <= 32) b = 0; else if (pairs <= 64) b = 1; else if (pairs <= 128) b = 2;
+        else if (pairs <= 4096) b = 3; else b = 4;
+        bucket_of[u] = b;
+        const int K = (b == 0) ? 1 : (b == 1) ? 2 : (b == 4) ? 8 : 4;
+        if (b >= 3) wide_need[b] = std::max(wide_need[b], (pairs + 32 * K - 1) / (32 * K));
+        P->e_row[u] = (int32_t)align_up((size_t)L + 1, 4);
+        P->row_max[b] = std::max(P->row_max[b], P->e_row[u]);
+        P->order[b].push_back(u);
+    }
+    size_t e_floats = 0, bp_words = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        const int b = bucket_of[u];
+        const int K = (b == 0) ? 1 : (b == 1) ? 2 : (b == 4) ? 8 : 4;
+        const int threads = (b >= 3) ? 32 * wide_need[b] : 32;
+        P->bp_pairs[u] = threads * K;
+        P->e_off[u] = (int64_t)e_floats;
+        e_floats += (size_t)h_t_len[u] * P->e_row[u];
+        P->bp_off[u] = (int64_t)bp_words;
+        bp_words += (size_t)((h_t_len[u] + 7) / 8) * P->bp_pairs[u];
+    }
+    for (int b = 0; b < kBuckets; ++b) P->wide_warps[b] = wide_need[b];
+    P->emit_bytes = align_up(e_floats * 4 + 16, 256);
+    P->bp_bytes = align_up(bp_words * 4 + 16, 256);
+
+    // device metadata blob
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) { delete P; return cuda_fail(ce, "cudaSetDevice"); }
+    cudaDeviceProp prop;
+    ce = cudaGetDeviceProperties(&prop, device);
+    if (ce != cudaSuccess) { delete P; return cuda_fail(ce, "cudaGetDeviceProperties"); }
+    P->sm_count = prop.multiProcessorCount;
+    std::vector<unsigned char> blob;
+    auto put = [&](const void* src, size_t bytes) -> size_t {
+        const size_t off = align_up(blob.size(), 16);
+        blob.resize(off + std::max<size_t>(bytes, 16));
+        if (bytes) memcpy(blob.data() + off, src, bytes);
+        return off;
+    };
+    const size_t o_t = put(P->t_off.data(), P->t_off.size() * 4);
+    const size_t o_l = put(P->l_off.data(), P->l_off.size() * 4);
+    const size_t o_lab = put(h_labels, (size_t)lsum * 4);
+    const size_t o_eo = put(P->e_off.data(), P->e_off.size() * 8);
+    const size_t o_er = put(P->e_row.data(), P->e_row.size() * 4);
+    const size_t o_bo = put(P->bp_off.data(), P->bp_off.size() * 8);
+    const size_t o_bpp = put(P->bp_pairs.data(), P->bp_pairs.size() * 4);
+    size_t o_ord[kBuckets];
+    for (int b = 0; b < kBuckets; ++b) o_ord[b] = put(P->order[b].data(), P->order[b].size() * 4);
+    ce = cudaMalloc(&P->d_meta, blob.size());
+    if (ce != cudaSuccess) { delete P; return cuda_fail(ce, "cudaMalloc(meta)"); }
+    ce = cudaMemcpy(P->d_meta, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { cudaFree(P->d_meta); delete P; return cuda_fail(ce, "cudaMemcpy(meta)"); }
+    unsigned char* d = static_cast<unsigned char*>(P->d_meta);
+    P->meta.n_utt = n_utt; P->meta.V = V; P->meta.mode = mode;
+    P->meta.t_off = reinterpret_cast<const int32_t*>(d + o_t);
+    P->meta.l_off = reinterpret_cast<const int32_t*>(d + o_l);
+    P->meta.labels = reinterpret_cast<const int32_t*>(d + o_lab);
+    P->meta.e_off = reinterpret_cast<const int64_t*>(d + o_eo);
+    P->meta.e_row = reinterpret_cast<const int32_t*>(d + o_er);
+    P->meta.bp_off = reinterpret_cast<const int64_t*>(d + o_bo);
+    P->meta.bp_pairs = reinterpret_cast<const int32_t*>(d + o_bpp);
+    for (int b = 0; b < kBuckets; ++b) P->d_order[b] = reinterpret_cast<const int32_t*>(d + o_ord[b]);
+    *out = P;
+    return LA_OK;
+}
+
+void la_plan_destroy(la_plan* P) {
+    if (!P) return;
+    cudaSetDevice(P->device);
+    if (P->d_meta) cudaFree(P->d_meta);
+    for (int i = 0; i < 2; ++i) {
+        if (P->d_stage[i]) cudaFree(P->d_stage[i]);
+        if (P->ev_copied[i]) cudaEventDestroy(P->ev_copied[i]);
+        if (P->ev_done[i]) cudaEventDestroy(P->ev_done[i]);
+    }
+    if (P->d_ws) cudaFree(P->d_ws);
+    if (P->d_out) cudaFree(P->d_out);
+    if (P->s_copy) cudaStreamDestroy(P->s_copy);
+    if (P->s_comp) cudaStreamDestroy(P->s_comp);
+    delete P;
+}
+
+size_t la_plan_workspace_bytes(const la_plan* P) { return P ? P->emit_bytes + P->bp_bytes : 0; }
+int64_t la_plan_total_frames(const la_plan* P) { return P ? P->total_T : 0; }
+int64_t la_plan_total_labels(const la_plan* P) { return P ? P->total_L : 0; }
+
+int la_plan_utt_layout(const la_plan* P, int utt, int64_t* emit_off_bytes, int32_t* row_floats,
+                       int64_t* bp_off_bytes, int32_t* pairs_padded) {
+    if (!P || utt < 0 || utt >= P->n_utt) return fail(LA_ERR_ARG, "bad utterance index");
+    if (emit_off_bytes) *emit_off_bytes = P->e_off[utt] * 4;
+    if (row_floats) *row_floats = P->e_row[utt];
+    if (bp_off_bytes) *bp_off_bytes = (int64_t)P->emit_bytes + P->bp_off[utt] * 4;
+    if (pairs_padded) *pairs_padded = P->bp_pairs[utt];
+    return LA_OK;
+}
+
+// rows [row0, row0 + n_rows) of the batch; d_logits points at row `row0`
+static int emit_rows(const la_plan* P, const float* d_logits, int64_t ld, const float* d_sil,
+                     int64_t ld_sil, void* d_ws, int64_t row0, int64_t n_rows, cudaStream_t stream);
+
+int la_emit(const la_plan* P, const float* d_logits, int64_t ld, const float* d_sil, int64_t ld_sil,
+            void* d_ws, void* stream) {
+    if (!P || !d_ws) return fail(LA_ERR_ARG, "null argument");
+    if (P->total_T == 0) return LA_OK;
+    if (!d_logits) return fail(LA_ERR_ARG, "null logits");
+    if (ld < P->V) return fail(LA_ERR_ARG, "row stride smaller than V");
+    if (P->mode == LA_MODE_LOGP && !d_sil) return fail(LA_ERR_ARG, "LA_MODE_LOGP needs the silence column");
+    if (reinterpret_cast<uintptr_t>(d_logits) & 15) return fail(LA_ERR_ARG, "logits base must be 16-byte aligned");
+    LA_CUDA(cudaSetDevice(P->device));
+    return emit_rows(P, d_logits, ld, d_sil, ld_sil, d_ws, 0, P->total_T, static_cast<cudaStream_t>(stream));
+}
+
+static int viterbi_impl(const la_plan* P, void* d_ws, int32_t* d_first, int32_t* d_last, double* d_score,
+                        int32_t* d_status, double* d_dp, void* stream) {
+    if (!P || !d_ws || !d_score || !d_status) return fail(LA_ERR_ARG, "null argument");
+    if (P->total_L > 0 && (!d_first || !d_last)) return fail(LA_ERR_ARG, "null output");
+    LA_CUDA(cudaSetDevice(P->device));
+    for (int b = 0; b < kBuckets; ++b) {
+        if (P->order[b].empty()) continue;
+        la::VitParams vp;
+        vp.m = P->meta;
+        vp.E = static_cast<const float*>(d_ws);
+        vp.bp = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(d_ws) + P->emit_bytes);
+        vp.order = P->d_order[b];
+        vp.n_order = (int)P->order[b].size();
+        vp.row_floats_max = P->row_max[b];
+        vp.chunk = la::viterbi_chunk_frames(P->row_max[b]);
+        vp.first = d_first; vp.last_plus1 = d_last; vp.score = d_score; vp.status = d_status;
+        vp.dp_dump = d_dp;
+        LA_CUDA(la::launch_viterbi(vp, b, P->wide_warps[b], static_cast<cudaStream_t>(stream)));
+    }
+    return LA_OK;
+}
+
+int la_viterbi(const la_plan* P, void* d_ws, int32_t* d_first, int32_t* d_last, double* d_score,
+               int32_t* d_status, void* stream) {
+    return viterbi_impl(P, d_ws, d_first, d_last, d_score, d_status, nullptr, stream);
+}
+
+int la_viterbi_debug(const la_plan* P, void* d_ws, int32_t* d_first, int32_t* d_last, double* d_score,
+                     int32_t* d_status, double* d_dp, void* stream) {
+    if (P && P->n_utt != 1) return fail(LA_ERR_ARG, "la_viterbi_debug takes a 1-utterance plan");
+    return viterbi_impl(P, d_ws, d_first, d_last, d_score, d_status, d_dp, stream);
+}
+
+int la_align(const la_plan* P, const float* d_logits, int64_t ld, void* d_ws, int32_t* d_first,
+             int32_t* d_last, double* d_score, int32_t* d_status, void* stream) {
+    if (P && P->mode == LA_MODE_LOGP) return fail(LA_ERR_ARG, "la_align needs LA_MODE_CTC or LA_MODE_CE");
+    int rc = la_emit(P, d_logits, ld, nullptr, 0, d_ws, stream);
+    if (rc) return rc;
+    return la_viterbi(P, d_ws, d_first, d_last, d_score, d_status, stream);
+}
+
+int la_align_host(la_plan* P, const float* h_logits, int64_t ld, int32_t* h_first, int32_t* h_last,
+                  double* h_score, int32_t* h_status, size_t staging_bytes) {
+    if (!P || !h_score || !h_status) return fail(LA_ERR_ARG, "null argument");
+    if (P->mode == LA_MODE_LOGP) return fail(LA_ERR_ARG, "la_align_host needs LA_MODE_CTC or LA_MODE_CE");
+    if (P->total_T > 0 && !h_logits) return fail(LA_ERR_ARG, "null logits");
+    if (ld < P->V) return fail(LA_ERR_ARG, "row stride smaller than V");
+    LA_CUDA(cudaSetDevice(P->device));
+    const size_t row_bytes = (size_t)ld * 4;
+    if (staging_bytes == 0) staging_bytes = (size_t)256 << 20;
+    size_t rows_per_stage = std::max<size_t>(1, staging_bytes / row_bytes);
+    rows_per_stage = std::min<size_t>(rows_per_stage, (size_t)std::max<int64_t>(P->total_T, 1));
+    // keep every stage base 16-byte aligned: row_bytes * rows must be a multiple of 16
+    while ((rows_per_stage * row_bytes) % 16 && rows_per_stage > 1) --rows_per_stage;
+    const size_t need = align_up(rows_per_stage * row_bytes + 16, 256);
+    if (!P->s_copy) {
+        LA_CUDA(cudaStreamCreateWithFlags(&P->s_copy, cudaStreamNonBlocking));
+        LA_CUDA(cudaStreamCreateWithFlags(&P->s_comp, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            LA_CUDA(cudaEventCreateWithFlags(&P->ev_copied[i], cudaEventDisableTiming));
+            LA_CUDA(cudaEventCreateWithFlags(&P->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    if (P->stage_bytes < need) {
+        for (int i = 0; i < 2; ++i) {
+            if (P->d_stage[i]) cudaFree(P->d_stage[i]);
+            P->d_stage[i] = nullptr;
+            LA_CUDA(cudaMalloc(&P->d_stage[i], need));
+        }
+        P->stage_bytes = need;
+    }
+    const size_t out_bytes = align_up((size_t)P->total_L * 4, 16) * 2 + align_up((size_t)P->n_utt * 8, 16) +
+                             align_up((size_t)P->n_utt * 4, 16) + 64;
+    if (!P->d_ws) LA_CUDA(cudaMalloc(&P->d_ws, la_plan_workspace_bytes(P)));
+    if (!P->d_out) LA_CUDA(cudaMalloc(&P->d_out, out_bytes));
+    unsigned char* o = static_cast<unsigned char*>(P->d_out);
+    int32_t* d_first = reinterpret_cast<int32_t*>(o);
+    int32_t* d_last = reinterpret_cast<int32_t*>(o + align_up((size_t)P->total_L * 4, 16));
+    double* d_score = reinterpret_cast<double*>(o + 2 * align_up((size_t)P->total_L * 4, 16));
+    int32_t* d_status = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(d_score) + align_up((size_t)P->n_utt * 8, 16));
+
+    // chunked H2D (copy stream) overlapped with K2 (compute stream), two staging buffers
+    int64_t row = 0;
+    int i = 0;
+    bool used[2] = {false, false};
+    while (row < P->total_T) {
+        const int64_t n = std::min<int64_t>((int64_t)rows_per_stage, P->total_T - row);
+        const int sbuf = i & 1;
+        if (used[sbuf]) LA_CUDA(cudaStreamWaitEvent(P->s_copy, P->ev_done[sbuf], 0));
+        LA_CUDA(cudaMemcpyAsync(P->d_stage[sbuf], h_logits + row * ld, (size_t)n * row_bytes,
+                                cudaMemcpyHostToDevice, P->s_copy));
+        LA_CUDA(cudaEventRecord(P->ev_copied[sbuf], P->s_copy));
+        LA_CUDA(cudaStreamWaitEvent(P->s_comp, P->ev_copied[sbuf], 0));
+        int rc = emit_rows(P, static_cast<const float*>(P->d_stage[sbuf]), ld, nullptr, 0, P->d_ws, row, n, P->s_comp);
+        if (rc) return rc;
+        LA_CUDA(cudaEventRecord(P->ev_done[sbuf], P->s_comp));
+        used[sbuf] = true;
+        row += n;
+        ++i;
+    }
+    int rc = la_viterbi(P, P->d_ws, d_first, d_last, d_score, d_status, P->s_comp);
+    if (rc) return rc;
+    if (P->total_L > 0) {
+        LA_CUDA(cudaMemcpyAsync(h_first, d_first, (size_t)P->total_L * 4, cudaMemcpyDeviceToHost, P->s_comp));
+        LA_CUDA(cudaMemcpyAsync(h_last, d_last, (size_t)P->total_L * 4, cudaMemcpyDeviceToHost, P->s_comp));
+    }
+    if (P->n_utt > 0) {
+        LA_CUDA(cudaMemcpyAsync(h_score, d_score, (size_t)P->n_utt * 8, cudaMemcpyDeviceToHost, P->s_comp));
+        LA_CUDA(cudaMemcpyAsync(h_status, d_status, (size_t)P->n_utt * 4, cudaMemcpyDeviceToHost, P->s_comp));
+    }
+    LA_CUDA(cudaStreamSynchronize(P->s_comp));
+    return LA_OK;
+}
+
+}  // extern "C"
+
+static int emit_rows(const la_plan* P, const float* d_logits, int64_t ld, const float* d_sil,
+                     int64_t ld_sil, void* d_ws, int64_t row0, int64_t n_rows, cudaStream_t stream) {
+    la::EmitParams ep;
+    ep.m = P->meta;
+    ep.logits = d_logits; ep.ld = ld; ep.sil = d_sil; ep.ld_sil = ld_sil;
+    ep.E = static_cast<float*>(d_ws);
+    ep.row0 = row0;
+    ep.n_rows = (int)n_rows;
+    LA_CUDA(la::launch_emit(ep, P->sm_count, stream));
+    return LA_OK;
+}

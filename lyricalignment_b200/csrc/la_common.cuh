@@ -1,0 +1,106 @@
+// la_common.cuh -- shared device helpers (mbarrier / bulk-copy PTX) and kernel parameter blocks.
+// sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace la {
+
+// ---------------------------------------------------------------------------------------
+// mbarrier + cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy; src/dst 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// batch metadata shared by the kernels (device pointers, owned by the plan)
+// ---------------------------------------------------------------------------------------
+struct BatchMeta {
+    int n_utt;
+    int V;
+    int mode;
+    const int32_t* t_off;    // [n_utt+1] first logits row of each utterance
+    const int32_t* l_off;    // [n_utt+1]
+    const int32_t* labels;   // [sum L] original logit columns
+    const int64_t* e_off;    // [n_utt] float offset of the emission rows in the workspace
+    const int32_t* e_row;    // [n_utt] floats per emission row = round_up(L+1, 4)
+    const int64_t* bp_off;   // [n_utt] uint32 offset of the packed backpointers in the workspace
+    const int32_t* bp_pairs; // [n_utt] padded pair count (words per 8-frame block)
+};
+
+struct EmitParams {
+    BatchMeta m;
+    const float* logits;   // points at batch row `row0`
+    int64_t ld;            // row stride in floats
+    const float* sil;      // LOGP mode only
+    int64_t ld_sil;
+    float* E;              // workspace emission area
+    int64_t row0;          // batch row index of logits row 0 (host path streams row ranges)
+    int n_rows;
+};
+
+struct VitParams {
+    BatchMeta m;
+    const float* E;
+    uint32_t* bp;
+    const int32_t* order;   // utterance ids of this bucket
+    int n_order;
+    int row_floats_max;     // widest emission row in the bucket (smem stage sizing)
+    int chunk;              // frames per TMA chunk
+    int32_t* first;
+    int32_t* last_plus1;
+    double* score;
+    int32_t* status;
+    double* dp_dump;        // debug/parity only: full fp64 table [T][2L+1] of a 1-utterance plan, or null
+};
+
+cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
+cudaError_t launch_viterbi(const VitParams& p, int bucket, int wide_warps, cudaStream_t stream);
+int viterbi_chunk_frames(int row_floats_max);
+
+constexpr double kFloor = -10000000.0;   // utils/alignment.py:144
+constexpr float kClip = -1000.0f;        // utils/alignment.py:132,134 / :18,20
+
+}  // namespace la

@@ -1,0 +1,264 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against oracle/ and the golden
+vectors the reference produced. Bit-exact for the DP (tables, step codes, indices); stated
+tolerances for the fp32 emission math."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import split_onoff
+
+pytestmark = pytest.mark.gpu
+
+import lyricalignment_b200 as la                              # noqa: E402
+from lyricalignment_b200 import alignment as A                # noqa: E402
+from lyricalignment_b200._lib import MODE_CE, MODE_CTC, MODE_LOGP   # noqa: E402
+
+
+def emission_tolerance(pred_row_sil, ctc):
+    """|kernel - exact| budget per frame: 2e-5 for the fp32 log-softmax, plus the absolute error
+    fp32 `log(1 - sigmoid(z))` carries by construction, ~2^-23 (1 + e^z) (the reference's own
+    chain has it too; SURVEY.md section 7 hard part 4)."""
+    z = pred_row_sil.astype(np.float64)
+    return 2e-5 + (2.0 ** -22 * (1.0 + np.exp(z)) if ctc else 0.0)
+
+
+def run_plan(pred, rows, mode, t_len=None):
+    """pred: [sumT, V] float32 ndarray; rows: list of label arrays -> (AlignResult, emissions, codes)."""
+    V = pred.shape[1]
+    l_len, cols = A._resolve_columns(rows, V - 2 if mode == MODE_CTC else V - 1)
+    t_len = np.asarray(t_len, np.int32)
+    plan = A.AlignPlan(mode, V, t_len, l_len, cols, 0)
+    res, ws = A._run_device(plan, torch.from_numpy(pred).cuda(), keep_workspace=True)
+    emis = [A.unpack_emissions(plan, ws, u) for u in range(len(rows))]
+    codes = [A.unpack_step_codes(plan, ws, u) for u in range(len(rows))]
+    plan.close()
+    return res, emis, codes
+
+
+def check_against_oracle(pred, rows, mode, t_len, res, emis, codes, tag=""):
+    """(1) emissions within tolerance of the fp64 oracle; (2) DP bit-exact vs the C oracle run
+    on the kernel's own emissions: step codes, first/last, score, status."""
+    ctc = mode == MODE_CTC
+    p, r0 = 0, 0
+    for u, lab in enumerate(rows):
+        T, L = int(t_len[u]), len(lab)
+        x = pred[r0:r0 + T]
+        if L and T:
+            e64, b64 = (oracle.emission_ctc_f64 if ctc else oracle.emission_ce_f64)(x)
+            want = np.concatenate([b64, e64[:, np.asarray(lab) - 1]], axis=1)
+            tol = emission_tolerance(x[:, -1], ctc)[:, None]
+            err = np.abs(emis[u] - want)
+            clipped = want <= -1000.0 + 1e-3
+            assert np.all((err <= tol) | clipped), (tag, u, float(err.max()))
+            o = _oracle_on_emissions(emis[u], lab)
+            assert int(res.status[u]) == o["status"], (tag, u)
+            S = 2 * L + 1
+            want_codes = (np.arange(S)[None, :] - o["bt"])[1:]
+            assert np.array_equal(codes[u][1:], want_codes), (tag, u)
+            if o["status"] == 0:
+                assert np.array_equal(res.first[p:p + L], o["first"]), (tag, u)
+                assert np.array_equal(res.last_plus1[p:p + L], o["last_plus1"]), (tag, u)
+            assert res.score[u] == o["score"], (tag, u)
+        else:
+            assert int(res.status[u]) == (1 if L == 0 else 2)
+        p += L
+        r0 += T
+
+
+def _oracle_on_emissions(e, lab):
+    """C oracle DP on the kernel's compact emission rows, preserving label repeats."""
+    uniq = {}
+    rel = np.array([uniq.setdefault(int(v), len(uniq) + 1) for v in lab], dtype=np.int64)
+    cols = np.zeros((e.shape[0], len(uniq)), np.float32)
+    for j, v in enumerate(rel):
+        cols[:, v - 1] = e[:, 1 + j]
+    return oracle.align_one(cols, np.ascontiguousarray(e[:, :1]), rel, want_tables=True)
+
+
+# ------------------------------------------------------------------------------------------
+def test_core_tables_bit_exact_vs_reference_golden(core_cases):
+    """run_viterbi_core boundary: every fp64 dp cell and every backpointer equal to what the
+    reference's numba kernel produced."""
+    for name, c in core_cases.items():
+        e, b, lab = c["emit"], c["blank"], c["label"]
+        T, S = e.shape[0], 2 * len(lab) + 1
+        dp = np.full((T, S), -10000000.0)
+        bt = np.zeros((T, S), dtype=np.int64)
+        dp[0][0] = b[0][0]
+        dp[0][1] = e[0][lab[0] - 1]
+        la.run_viterbi_core(dp, bt, e, b, lab)
+        assert np.array_equal(bt, c["bt"]), name
+        assert np.array_equal(dp, c["dp"]), name
+
+
+def test_decode_golden(decode_cases):
+    for name, c in decode_cases.items():
+        ctc = bool(int(c["ctc"]))
+        fn = la.perform_viterbi_ctc if ctc else la.perform_viterbi
+        want = split_onoff(c["onoff"], c["lens"])
+        got_dev = fn(torch.from_numpy(c["pred"]).cuda(), torch.from_numpy(c["labels"]))
+        got_host = fn(torch.from_numpy(c["pred"]), c["labels"].tolist())
+        assert got_dev == got_host, name
+        if not name.startswith("grid_"):     # exact-tie grids may flip on a 1-ulp emission difference
+            assert got_dev == want, name
+        # emissions / score / codes against the reference's recorded values
+        B, T, V = c["pred"].shape
+        rows = A._label_rows(c["labels"])
+        res, emis, codes = run_plan(c["pred"].reshape(B * T, V), rows, MODE_CTC if ctc else MODE_CE, [T] * B)
+        pe = 0
+        for u, lab in enumerate(rows):
+            L = len(lab)
+            ref_e = c["emit_at_labels"][pe:pe + T * L].reshape(T, L); pe += T * L
+            tol = 2.0 * emission_tolerance(c["pred"][u][:, -1], ctc)[:, None]
+            if not name.startswith("sat_"):
+                assert np.all(np.abs(emis[u][:, 1:] - ref_e) <= tol), name
+                assert np.all(np.abs(emis[u][:, 0] - c["blank"][u]) <= tol[:, 0]), name
+            assert res.score[u] == pytest.approx(c["score"][u], rel=1e-5), name
+        check_against_oracle(c["pred"].reshape(B * T, V), rows, MODE_CTC if ctc else MODE_CE, [T] * B,
+                             res, emis, codes, name)
+
+
+def test_saturated_silence_matches_reference_exactly(decode_cases):
+    """z_sil = +40 -> 1 - s == 0 -> log = -inf -> clip(-1000) exactly; -120 -> log s clipped."""
+    for name in ("sat_pos40", "sat_neg120"):
+        c = decode_cases[name]
+        B, T, V = c["pred"].shape
+        rows = A._label_rows(c["labels"])
+        res, emis, _ = run_plan(c["pred"].reshape(B * T, V), rows, MODE_CTC, [T] * B)
+        np.testing.assert_array_equal(emis[0][:, 0], c["blank"][0])
+        if name == "sat_pos40":
+            assert np.all(emis[0][:, 1:] == -1000.0)
+
+
+def test_error_behaviour_matches_reference():
+    z = torch.zeros((1, 4, 12)).cuda()
+    with pytest.raises(IndexError):
+        la.perform_viterbi_ctc(z, torch.tensor([[-100, -100]]))
+    with pytest.raises(ValueError):
+        la.perform_viterbi_ctc(z, torch.tensor([[3, 4, 5, 6, 7]]))
+    with pytest.raises(ValueError):
+        la.perform_viterbi_ctc(z[:, :2], torch.tensor([[3, 3]]))
+    with pytest.raises(ValueError):
+        la.perform_viterbi(z, [[3, 4, 5, 6, 7]])
+    assert la.perform_viterbi_ctc(z[:, :1], torch.tensor([[3]])) == [[[0.0, 0.02]]]
+    # first failing utterance in batch order decides, as in the reference's loop
+    z2 = torch.zeros((2, 4, 12)).cuda()
+    with pytest.raises(ValueError):
+        la.perform_viterbi_ctc(z2, [[3, 4, 5, 6, 7], []])
+    with pytest.raises(IndexError):
+        la.perform_viterbi_ctc(z2, [[], [3, 4, 5, 6, 7]])
+
+
+def _rand_rows(rng, n, lmin, lmax, vmax, p_rep=0.1):
+    rows = []
+    for _ in range(n):
+        L = int(rng.integers(lmin, lmax + 1))
+        r = []
+        for j in range(L):
+            r.append(r[-1] if j and rng.random() < p_rep else int(rng.integers(1, vmax + 1)))
+        rows.append(np.array(r, dtype=np.int64))
+    return rows
+
+
+@pytest.mark.parametrize("mode", [MODE_CTC, MODE_CE])
+def test_ragged_batch_all_buckets(mode):
+    """One plan mixing every launch shape: 1/2/4 pairs per lane (warp per utterance) and the
+    CTA-wide path, ragged T, odd V so rows are only 4-byte aligned."""
+    rng = np.random.default_rng(5 + mode)
+    V = 1237
+    specs = [(57, 3), (200, 31), (333, 32), (129, 60), (400, 63), (97, 64), (250, 127), (260, 128),
+             (300, 200), (1, 1), (16, 5), (17, 7), (610, 300), (9, 0)]
+    rows, t_len = [], []
+    for T, L in specs:
+        rows += _rand_rows(rng, 1, L, L, V - 2) if L else [np.zeros(0, np.int64)]
+        t_len.append(T)
+    pred = (2.0 * rng.standard_normal((sum(t_len), V))).astype(np.float32)
+    pred[:, -1] = rng.uniform(-6, 6, size=pred.shape[0])
+    res, emis, codes = run_plan(pred, rows, mode, t_len)
+    check_against_oracle(pred, rows, mode, t_len, res, emis, codes, f"ragged{mode}")
+    assert int(res.status[-1]) == 1
+
+
+@pytest.mark.parametrize("mode", [MODE_CTC, MODE_CE])
+def test_full_vocab_clip_vs_oracle_end_to_end(mode):
+    """V = 21129 (the real head width), one Opencpop-sized clip: full chain vs the oracle's
+    reference-order fp32 chain -- indices identical, score within 1e-5 relative."""
+    rng = np.random.default_rng(11 + mode)
+    T, V, L = 300, 21129, 24
+    rows = _rand_rows(rng, 1, L, L, 402)
+    pred = (2.0 * rng.standard_normal((1, T, V))).astype(np.float32)
+    bounds = np.sort(rng.choice(np.arange(1, T), size=2 * L, replace=False))
+    seg = np.searchsorted(bounds, np.arange(T), side="right")
+    sil_col = V - 1 if mode == MODE_CTC else 0
+    for t in range(T):
+        if seg[t] % 2:
+            pred[0, t, rows[0][seg[t] // 2]] += 9.0
+            pred[0, t, sil_col] -= 2.0
+        else:
+            pred[0, t, sil_col] += 4.0 if mode == MODE_CTC else 9.0
+    fn, ofn = (la.perform_viterbi_ctc, oracle.perform_viterbi_ctc) if mode == MODE_CTC else (la.perform_viterbi, oracle.perform_viterbi)
+    want = ofn(pred, [rows[0].tolist()])
+    assert fn(torch.from_numpy(pred).cuda(), [rows[0].tolist()]) == want
+    assert fn(torch.from_numpy(pred), [rows[0].tolist()]) == want            # host-buffer path
+    res, emis, codes = run_plan(pred[0], rows, mode, [T])
+    check_against_oracle(pred[0], rows, mode, [T], res, emis, codes, "fullV")
+
+
+def test_host_path_streams_in_several_stages():
+    rng = np.random.default_rng(3)
+    V, B, T = 515, 6, 90
+    rows = _rand_rows(rng, B, 4, 30, V - 2)
+    pred = torch.from_numpy((2.0 * rng.standard_normal((B * T, V))).astype(np.float32))
+    l_len, cols = A._resolve_columns(rows, V - 2)
+    plan = A.AlignPlan(MODE_CTC, V, np.full(B, T, np.int32), l_len, cols, 0)
+    dev = A._run_device(plan, pred.cuda())
+    host = A._run_host(plan, pred.pin_memory(), staging_bytes=37 * V * 4)   # 37 rows per stage: splits utterances
+    plan.close()
+    for f in ("first", "last_plus1", "score", "status"):
+        assert np.array_equal(getattr(dev, f), getattr(host, f)), f
+
+
+def test_strided_and_misaligned_input():
+    rng = np.random.default_rng(4)
+    B, T, V = 2, 50, 101
+    big = torch.from_numpy((2.0 * rng.standard_normal((B, T, V + 3))).astype(np.float32)).cuda()
+    view = big[:, :, 1:V + 1]                                   # non-contiguous, 4-byte-offset base
+    rows = _rand_rows(rng, B, 5, 9, V - 2)
+    got = la.perform_viterbi_ctc(view, [r.tolist() for r in rows])
+    assert got == la.perform_viterbi_ctc(view.contiguous().cpu(), [r.tolist() for r in rows])
+    assert got == oracle.perform_viterbi_ctc(view.cpu().numpy(), [r.tolist() for r in rows])
+
+
+def test_long_form_trellis_bit_exact():
+    """BASELINE config 4: 15 000 frames x 600 syllables (CTA-wide kernel, HBM-tiled backpointers).
+    Small V keeps the logits small; the DP is checked cell-for-cell on step codes."""
+    rng = np.random.default_rng(8)
+    T, L, V = 15000, 600, 410
+    rows = _rand_rows(rng, 1, L, L, 402, p_rep=0.05)
+    pred = (1.5 * rng.standard_normal((T, V))).astype(np.float32)
+    seg = np.minimum((np.arange(T) * (2 * L + 1)) // T, 2 * L)
+    lab_t = np.where(seg % 2 == 1, rows[0][np.minimum(seg // 2, L - 1)], -1)
+    idx = np.nonzero(lab_t >= 0)[0]
+    pred[idx, lab_t[idx]] += 6.0
+    pred[:, -1] = np.where(seg % 2 == 0, 3.0, -3.0)
+    res, emis, codes = run_plan(pred, rows, MODE_CTC, [T])
+    check_against_oracle(pred, rows, MODE_CTC, [T], res, emis, codes, "longform")
+    assert int(res.status[0]) == 0
+    assert np.all(res.first[1:] >= res.last_plus1[:-1] - 0) and np.all(res.last_plus1 > res.first)
+
+
+def test_quantised_ties_bit_exact():
+    """Emissions that are multiples of 2^-3: fp64 path sums tie exactly all over the trellis, so
+    any deviation from the reference's comparison forms / branch order shows up in the codes."""
+    rng = np.random.default_rng(9)
+    for L, T in [(9, 70), (40, 200), (100, 350), (300, 900)]:
+        lab = _rand_rows(rng, 1, L, L, 60, p_rep=0.3)[0]
+        e = (rng.integers(-24, 1, size=(T, 60)) / 8.0).astype(np.float32)
+        b = (rng.integers(-24, 1, size=(T, 1)) / 8.0).astype(np.float32)
+        S = 2 * L + 1
+        dp = np.full((T, S), -10000000.0); bt = np.zeros((T, S), np.int64)
+        dp[0][0] = b[0][0]; dp[0][1] = e[0][lab[0] - 1]
+        la.run_viterbi_core(dp, bt, e, b, lab)
+        o = oracle.align_one(e, b, lab, want_tables=True)
+        assert np.array_equal(bt[1:], o["bt"][1:]) and np.array_equal(dp, o["dp"])
