@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- aligned audio-seconds per second of the alignment decode path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): an Opencpop-test-shaped batch of 2,000 synthetic clips of
+5-15 s, head width V = 21129 (fp32 logits, 84.5 KB per 20 ms frame), CTC-flavour decode
+(perform_viterbi_ctc) against 2.4 char/s pinyin-class lyrics. One "step" = one pass of the hot
+path (K2 fused log-softmax + gather, K3 Viterbi + backtrace) over the whole batch.
+
+  value  : whole-job audio-s/s with the logits resident in HBM (84.5 GB per GPU, >> L2, so every
+           step streams from HBM); CUDA-event timed, max over ranks.
+  e2e    : the same metric through the reference-facing call `perform_viterbi_ctc(cpu_tensor,
+           labels)`, batch size 1 as in inference_alignment.py, logits in PINNED HOST memory --
+           H2D copy of every clip's logits and D2H of its alignment inside the timed region.
+  roofline / cpu_baseline : see DESIGN.md ("Measurement").
+With N > 1 (torchrun) every rank owns its own 2,000 clips (weak scaling) and the step ends with
+the NCCL gather of all alignments to rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CLIPS = 2000
+POOL_CLIPS = 100          # pinned host pool for the e2e leg (~4.2 GB), recycled 20x per step
+CPU_SAMPLE_CLIPS = 16
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's own decode on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_decode_fn():
+    """Returns (fn(pred_cpu[1,T,V] tensor, labels) -> onoff, kind). The unmodified reference when
+    its tree is mounted (dev container), else the oracle port: the reference's torch CPU emission
+    chain (all intra-op threads, as shipped) + the C restatement of its DP."""
+    from oracle import ref_shim
+    if ref_shim.available():
+        ref = ref_shim.load()
+        return ref.perform_viterbi_ctc, "reference"
+    import torch.nn.functional as F
+    import oracle
+
+    def port(pred, labels, hop=0.02):
+        lp = F.log_softmax(pred[:, :, 1:-1], dim=2)                   # utils/alignment.py:123
+        s = torch.sigmoid(pred[:, :, -1:])                            # :125
+        emit = torch.clip(lp + torch.log(1.0 - s), min=-1000)         # :126-132
+        blank = torch.clip(torch.log(s), min=-1000)                   # :128,134
+        out = []
+        for i in range(pred.shape[0]):
+            lab = np.array([x for x in labels[i] if x != -100], dtype=np.int64)
+            r = oracle.align_one(emit[i].numpy(), blank[i].numpy(), lab)
+            assert r["status"] == 0
+            out.append([[float(int(a)) * hop, float(int(b)) * hop] for a, b in zip(r["first"], r["last_plus1"])])
+        return out
+    return port, "port"
+
+
+def time_cpu(pool_pred, pool_labels, pool_dur, n_clips, repeats):
+    fn, kind = cpu_decode_fn()
+    fn(pool_pred[0][:, :8], [pool_labels[0][:1].tolist()])            # warm numba / libs
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for i in range(n_clips):
+            fn(pool_pred[i], [pool_labels[i].tolist()])
+        times.append(time.perf_counter() - t0)
+    secs = float(sum(pool_dur[:n_clips]))
+    return secs / statistics.median(times), kind, statistics.median(times)
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=N_CLIPS)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    from lyricalignment_b200 import synth
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        run_reference_arm(args, synth)
+        return
+
+    import torch.distributed as dist
+    from lyricalignment_b200 import _lib, alignment as A, sharded
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    # ---- workload: every rank owns its own clips (weak scaling) ----------------------------
+    batch = synth.opencpop_shaped(args.clips, seed=114514 + rank)
+    V = synth.V_HEAD
+    total_T = int(batch.t_len.sum())
+    logits = synth.planted_logits(batch, V, ctc=True, device=dev, seed=114514 + rank)
+    l_len, cols = A._resolve_columns(batch.labels, V - 2)
+    plan = A.AlignPlan(A.MODE_CTC, V, batch.t_len, l_len, cols, local_rank)
+    ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
+    first = torch.empty(plan.total_labels, dtype=torch.int32, device=dev)
+    last = torch.empty(plan.total_labels, dtype=torch.int32, device=dev)
+    score = torch.empty(plan.n_utt, dtype=torch.float64, device=dev)
+    status = torch.empty(plan.n_utt, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def step(ev_a=None, ev_b=None):
+        if ev_a is not None:
+            ev_a.record()
+        _lib.check(lib.la_emit(plan.handle, logits.data_ptr(), V, None, 0, ws.data_ptr(), stream), "la_emit")
+        if ev_b is not None:
+            ev_b.record()
+        _lib.check(lib.la_viterbi(plan.handle, ws.data_ptr(), first.data_ptr(), last.data_ptr(),
+                                  score.data_ptr(), status.data_ptr(), stream), "la_viterbi")
+        if world > 1:
+            res = A.AlignResult(first, last, score, status, l_len)
+            gather_device(res, dev, dist)
+
+    def gather_device(res, dev, dist):
+        # NCCL gather of the alignments to rank 0 (payload stays on the device until rank 0 reads it)
+        payload = torch.cat([res.first, res.last_plus1, res.status, res.score.view(torch.int32)])
+        out = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
+        dist.gather(payload, out, dst=0)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    assert int(status.max().item()) == 0, "synthetic clips must all be feasible"
+
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    t_start.record()
+    for k in range(args.steps):
+        step(*ev[k])
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = t_start.elapsed_time(t_end)
+    emit_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    audio_s = torch.tensor([batch.audio_seconds], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(audio_s, op=dist.ReduceOp.SUM)
+    value = float(audio_s.item()) * args.steps / (ms_total / 1e3)
+
+    # ---- roofline of the dominant kernel (K2) ----------------------------------------------
+    peak, peak_src = measured_peaks()
+    algo_bytes = 4.0 * total_T * V + 4.0 * float(np.sum(batch.t_len.astype(np.int64) * (l_len + 1)))
+    achieved = algo_bytes / (emit_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "la::emit_kernel<CTC> (K2 fused log-softmax + gather)", "bound": "hbm",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel_ms": round(emit_ms, 4)}
+
+    # ---- e2e + cpu baseline on rank 0's pinned pool ----------------------------------------
+    e2e, cpu = None, None
+    pool_n = min(POOL_CLIPS, args.clips)
+    pool_rows = int(batch.t_len[:pool_n].sum())
+    if not args.skip_e2e:
+        host = torch.empty((pool_rows, V), dtype=torch.float32).pin_memory()
+        host.copy_(logits[:pool_rows])
+        torch.cuda.synchronize()
+        offs = np.concatenate([[0], np.cumsum(batch.t_len[:pool_n])])
+        pool_pred = [host[offs[i]:offs[i + 1]].unsqueeze(0) for i in range(pool_n)]
+        import lyricalignment_b200 as la
+        n_calls = args.clips
+        lab_sets = [synth.opencpop_shaped(pool_n, seed=7000 + 31 * rank + j).labels for j in range((n_calls + pool_n - 1) // pool_n)]
+        # labels drawn for other durations may be too long for this clip: keep them feasible
+        def lab_for(i):
+            lab = lab_sets[i // pool_n][i % pool_n]
+            return lab[:max(1, int(batch.t_len[i % pool_n]) // 3)]
+
+        def e2e_step():
+            tot = 0
+            for i in range(n_calls):
+                out = la.perform_viterbi_ctc(pool_pred[i % pool_n], [lab_for(i).tolist()])
+                tot += len(out[0])
+            return tot
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            n_lab = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_audio = float(sum(batch.durations[i % pool_n] for i in range(n_calls))) * world
+        h2d = float(sum(int(batch.t_len[i % pool_n]) for i in range(n_calls))) * V * 4
+        e2e = {"value": round(e2e_audio * args.e2e_steps / float(tt.item()), 1), "unit": "audio-s/s",
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": float(n_lab * 8 + n_calls * 12) * world,
+               "steps": args.e2e_steps,
+               "call": "lyricalignment_b200.perform_viterbi_ctc(pinned_cpu_tensor[1,T,V], labels), one call per clip"}
+        if rank == 0 and not args.skip_cpu:
+            n_cpu = min(CPU_SAMPLE_CLIPS, pool_n)
+            v, kind, secs = time_cpu(pool_pred, batch.labels, batch.durations, n_cpu, 3)
+            cpu = {"value": round(v, 1), "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": kind,
+                   "sample": f"first {n_cpu} clips of the workload ({sum(batch.durations[:n_cpu]):.0f} audio-s), "
+                             f"median of 3 passes, {secs:.2f} s per pass, host cpu_count={os.cpu_count()}"}
+
+    if rank == 0:
+        line = {
+            "metric": "aligned audio-sec/sec (alignment decode path)", "value": round(value, 1), "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 emissions / f64 DP", "data": "synthetic",
+            "config": {"workload": f"configs[1]: Opencpop-test-shaped batch, {args.clips} clips of 5-15 s per GPU, "
+                                   f"V=21129 CTC decode, {plan.total_labels} syllables, {total_T} frames",
+                       "l2_policy": f"inputs larger than L2 ({4.0 * total_T * V / 1e9:.1f} GB of logits resident in HBM per GPU)",
+                       "parallelism": f"utterance-sharded x{world}" + (", NCCL gather of alignments in the step" if world > 1 else "")},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": plan.num_launches * args.steps, "clocks": clk,
+        }
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference_arm(args, synth):
+    """--impl reference: the reference's CPU decode on the host cores, bounded sample per step."""
+    torch.manual_seed(0)
+    n = CPU_SAMPLE_CLIPS
+    batch = synth.opencpop_shaped(args.clips, seed=114514)
+    sub = synth.ClipBatch(batch.durations[:n], batch.n_samples[:n], batch.t_len[:n], batch.labels[:n])
+    pred = synth.planted_logits(sub, synth.V_HEAD, ctc=True, device="cpu", seed=114514)
+    offs = np.concatenate([[0], np.cumsum(sub.t_len)])
+    pool = [pred[offs[i]:offs[i + 1]].unsqueeze(0) for i in range(n)]
+    fn, kind = cpu_decode_fn()
+    fn(pool[0][:, :8], [sub.labels[0][:1].tolist()])
+
+    def step():
+        for i in range(n):
+            fn(pool[i], [sub.labels[i].tolist()])
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = sub.audio_seconds * args.steps / dt
+    sample = (f"each step = first {n} clips of the workload ({sub.audio_seconds:.0f} audio-s); "
+              f"host cpu_count={os.cpu_count()}")
+    cpu = {"value": round(value, 1), "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample}
+    print(json.dumps({
+        "impl": "reference", "metric": "aligned audio-sec/sec (alignment decode path)", "value": round(value, 1),
+        "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 emissions / f64 DP", "data": "synthetic",
+        "config": {"workload": f"configs[1]: Opencpop-test-shaped batch, {args.clips} clips of 5-15 s, V=21129 CTC decode",
+                   "sample": sample},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(value, 1), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    main()

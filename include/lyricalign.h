@@ -78,6 +78,8 @@ void la_plan_destroy(la_plan* plan);
 size_t la_plan_workspace_bytes(const la_plan* plan);
 int64_t la_plan_total_frames(const la_plan* plan);
 int64_t la_plan_total_labels(const la_plan* plan);
+/* kernels one la_align() enqueues for this plan: 1 (K2) + one K3 launch per non-empty L bucket */
+int la_plan_num_launches(const la_plan* plan);
 /* introspection for tests: where utterance u's emission rows / packed backpointers live in
  * the workspace. emit: float32 [T_u][row_floats], column 0 = blank/silence, column 1+l =
  * label l. bp: uint32 [ceil(T_u/8)][pairs_padded], nibble (t%8) of word [t/8][i] =
@@ -115,8 +117,9 @@ int la_align(const la_plan* plan, const float* d_logits, int64_t ld, void* d_wor
 
 /* ---- same, HOST buffers (the reference's actual call: logits already `.cpu()`ed,
  * inference_alignment.py:161-166). Streams the logits through a double-buffered device
- * staging area owned by the plan (allocated on first use, `staging_bytes` each, 0 = default
- * 256 MiB) overlapping H2D copies with K2; results are copied back before returning.
+ * staging area owned by a per-device library context (grown on first use and reused across
+ * plans; `staging_bytes` each, 0 = default 16 MiB) overlapping H2D copies with K2; results are
+ * copied back before returning. Calls on one device are serialised by the context's mutex.
  * h_logits should be pinned for full PCIe rate. */
 int la_align_host(la_plan* plan, const float* h_logits, int64_t ld, int32_t* h_first,
                   int32_t* h_last_plus1, double* h_score, int32_t* h_status,

@@ -24,6 +24,7 @@ SIGNATURES = {
     "la_plan_workspace_bytes": (_sz, [_vp]),
     "la_plan_total_frames": (_i64, [_vp]),
     "la_plan_total_labels": (_i64, [_vp]),
+    "la_plan_num_launches": (_c_int, [_vp]),
     "la_plan_utt_layout": (_c_int, [_vp, _c_int, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_int32),
                                     ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_int32)]),
     "la_emit": (_c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),

@@ -77,6 +77,7 @@ class AlignPlan:
         self.total_frames = int(lib.la_plan_total_frames(self._h))
         self.total_labels = int(lib.la_plan_total_labels(self._h))
         self.workspace_bytes = int(lib.la_plan_workspace_bytes(self._h))
+        self.num_launches = int(lib.la_plan_num_launches(self._h))
 
     @property
     def handle(self):

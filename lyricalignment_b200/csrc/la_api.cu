@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -39,14 +40,24 @@ struct la_plan {
     void* d_meta = nullptr;
     la::BatchMeta meta{};
     const int32_t* d_order[kBuckets] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    // host-path staging (la_align_host)
+};
+
+// Host-path context (la_align_host): one per device, grown on demand, reused across plans so a
+// per-clip call (the reference's batch size 1) pays no cudaMalloc after the first.
+struct HostCtx {
+    std::mutex mu;
     void* d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
     void* d_ws = nullptr;
+    size_t ws_bytes = 0;
     void* d_out = nullptr;
+    size_t out_bytes = 0;
+    void* h_out = nullptr;      // pinned bounce buffer for the results
+    size_t h_out_bytes = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
+static HostCtx g_host[64];
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -163,21 +174,18 @@ void la_plan_destroy(la_plan* P) {
     if (!P) return;
     cudaSetDevice(P->device);
     if (P->d_meta) cudaFree(P->d_meta);
-    for (int i = 0; i < 2; ++i) {
-        if (P->d_stage[i]) cudaFree(P->d_stage[i]);
-        if (P->ev_copied[i]) cudaEventDestroy(P->ev_copied[i]);
-        if (P->ev_done[i]) cudaEventDestroy(P->ev_done[i]);
-    }
-    if (P->d_ws) cudaFree(P->d_ws);
-    if (P->d_out) cudaFree(P->d_out);
-    if (P->s_copy) cudaStreamDestroy(P->s_copy);
-    if (P->s_comp) cudaStreamDestroy(P->s_comp);
     delete P;
 }
 
 size_t la_plan_workspace_bytes(const la_plan* P) { return P ? P->emit_bytes + P->bp_bytes : 0; }
 int64_t la_plan_total_frames(const la_plan* P) { return P ? P->total_T : 0; }
 int64_t la_plan_total_labels(const la_plan* P) { return P ? P->total_L : 0; }
+int la_plan_num_launches(const la_plan* P) {
+    if (!P) return 0;
+    int n = P->total_T > 0 ? 1 : 0;
+    for (int b = 0; b < kBuckets; ++b) n += P->order[b].empty() ? 0 : 1;
+    return n;
+}
 
 int la_plan_utt_layout(const la_plan* P, int utt, int64_t* emit_off_bytes, int32_t* row_floats,
                        int64_t* bp_off_bytes, int32_t* pairs_padded) {
@@ -246,45 +254,67 @@ int la_align(const la_plan* P, const float* d_logits, int64_t ld, void* d_ws, in
     return la_viterbi(P, d_ws, d_first, d_last, d_score, d_status, stream);
 }
 
+static int grow(void** p, size_t* have, size_t need) {
+    if (*have >= need) return LA_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    LA_CUDA(cudaMalloc(p, need));
+    *have = need;
+    return LA_OK;
+}
+
 int la_align_host(la_plan* P, const float* h_logits, int64_t ld, int32_t* h_first, int32_t* h_last,
                   double* h_score, int32_t* h_status, size_t staging_bytes) {
     if (!P || !h_score || !h_status) return fail(LA_ERR_ARG, "null argument");
     if (P->mode == LA_MODE_LOGP) return fail(LA_ERR_ARG, "la_align_host needs LA_MODE_CTC or LA_MODE_CE");
     if (P->total_T > 0 && !h_logits) return fail(LA_ERR_ARG, "null logits");
+    if (P->total_L > 0 && (!h_first || !h_last)) return fail(LA_ERR_ARG, "null output");
     if (ld < P->V) return fail(LA_ERR_ARG, "row stride smaller than V");
+    if (P->device < 0 || P->device >= 64) return fail(LA_ERR_ARG, "device index out of range");
     LA_CUDA(cudaSetDevice(P->device));
+    HostCtx& C = g_host[P->device];
+    std::lock_guard<std::mutex> lock(C.mu);
     const size_t row_bytes = (size_t)ld * 4;
-    if (staging_bytes == 0) staging_bytes = (size_t)256 << 20;
+    if (staging_bytes == 0) staging_bytes = (size_t)16 << 20;
     size_t rows_per_stage = std::max<size_t>(1, staging_bytes / row_bytes);
     rows_per_stage = std::min<size_t>(rows_per_stage, (size_t)std::max<int64_t>(P->total_T, 1));
-    // keep every stage base 16-byte aligned: row_bytes * rows must be a multiple of 16
-    while ((rows_per_stage * row_bytes) % 16 && rows_per_stage > 1) --rows_per_stage;
+    if (!C.s_copy) {
+        LA_CUDA(cudaStreamCreateWithFlags(&C.s_copy, cudaStreamNonBlocking));
+        LA_CUDA(cudaStreamCreateWithFlags(&C.s_comp, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            LA_CUDA(cudaEventCreateWithFlags(&C.ev_copied[i], cudaEventDisableTiming));
+            LA_CUDA(cudaEventCreateWithFlags(&C.ev_done[i], cudaEventDisableTiming));
+        }
+    }
     const size_t need = align_up(rows_per_stage * row_bytes + 16, 256);
-    if (!P->s_copy) {
-        LA_CUDA(cudaStreamCreateWithFlags(&P->s_copy, cudaStreamNonBlocking));
-        LA_CUDA(cudaStreamCreateWithFlags(&P->s_comp, cudaStreamNonBlocking));
+    if (C.stage_bytes < need) {
         for (int i = 0; i < 2; ++i) {
-            LA_CUDA(cudaEventCreateWithFlags(&P->ev_copied[i], cudaEventDisableTiming));
-            LA_CUDA(cudaEventCreateWithFlags(&P->ev_done[i], cudaEventDisableTiming));
+            if (C.d_stage[i]) cudaFree(C.d_stage[i]);
+            C.d_stage[i] = nullptr;
         }
+        C.stage_bytes = 0;
+        for (int i = 0; i < 2; ++i) LA_CUDA(cudaMalloc(&C.d_stage[i], need));
+        C.stage_bytes = need;
     }
-    if (P->stage_bytes < need) {
-        for (int i = 0; i < 2; ++i) {
-            if (P->d_stage[i]) cudaFree(P->d_stage[i]);
-            P->d_stage[i] = nullptr;
-            LA_CUDA(cudaMalloc(&P->d_stage[i], need));
-        }
-        P->stage_bytes = need;
+    const size_t lab_bytes = align_up((size_t)P->total_L * 4, 16);
+    const size_t sc_bytes = align_up((size_t)P->n_utt * 8, 16);
+    const size_t st_bytes = align_up((size_t)P->n_utt * 4, 16);
+    const size_t out_bytes = 2 * lab_bytes + sc_bytes + st_bytes + 64;
+    int rc = grow(&C.d_ws, &C.ws_bytes, la_plan_workspace_bytes(P));
+    if (rc) return rc;
+    rc = grow(&C.d_out, &C.out_bytes, out_bytes);
+    if (rc) return rc;
+    if (C.h_out_bytes < out_bytes) {
+        if (C.h_out) cudaFreeHost(C.h_out);
+        C.h_out = nullptr; C.h_out_bytes = 0;
+        LA_CUDA(cudaMallocHost(&C.h_out, out_bytes));
+        C.h_out_bytes = out_bytes;
     }
-    const size_t out_bytes = align_up((size_t)P->total_L * 4, 16) * 2 + align_up((size_t)P->n_utt * 8, 16) +
-                             align_up((size_t)P->n_utt * 4, 16) + 64;
-    if (!P->d_ws) LA_CUDA(cudaMalloc(&P->d_ws, la_plan_workspace_bytes(P)));
-    if (!P->d_out) LA_CUDA(cudaMalloc(&P->d_out, out_bytes));
-    unsigned char* o = static_cast<unsigned char*>(P->d_out);
+    unsigned char* o = static_cast<unsigned char*>(C.d_out);
     int32_t* d_first = reinterpret_cast<int32_t*>(o);
-    int32_t* d_last = reinterpret_cast<int32_t*>(o + align_up((size_t)P->total_L * 4, 16));
-    double* d_score = reinterpret_cast<double*>(o + 2 * align_up((size_t)P->total_L * 4, 16));
-    int32_t* d_status = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(d_score) + align_up((size_t)P->n_utt * 8, 16));
+    int32_t* d_last = reinterpret_cast<int32_t*>(o + lab_bytes);
+    double* d_score = reinterpret_cast<double*>(o + 2 * lab_bytes);
+    int32_t* d_status = reinterpret_cast<int32_t*>(o + 2 * lab_bytes + sc_bytes);
 
     // chunked H2D (copy stream) overlapped with K2 (compute stream), two staging buffers
     int64_t row = 0;
@@ -293,29 +323,32 @@ int la_align_host(la_plan* P, const float* h_logits, int64_t ld, int32_t* h_firs
     while (row < P->total_T) {
         const int64_t n = std::min<int64_t>((int64_t)rows_per_stage, P->total_T - row);
         const int sbuf = i & 1;
-        if (used[sbuf]) LA_CUDA(cudaStreamWaitEvent(P->s_copy, P->ev_done[sbuf], 0));
-        LA_CUDA(cudaMemcpyAsync(P->d_stage[sbuf], h_logits + row * ld, (size_t)n * row_bytes,
-                                cudaMemcpyHostToDevice, P->s_copy));
-        LA_CUDA(cudaEventRecord(P->ev_copied[sbuf], P->s_copy));
-        LA_CUDA(cudaStreamWaitEvent(P->s_comp, P->ev_copied[sbuf], 0));
-        int rc = emit_rows(P, static_cast<const float*>(P->d_stage[sbuf]), ld, nullptr, 0, P->d_ws, row, n, P->s_comp);
+        if (used[sbuf]) LA_CUDA(cudaStreamWaitEvent(C.s_copy, C.ev_done[sbuf], 0));
+        LA_CUDA(cudaMemcpyAsync(C.d_stage[sbuf], h_logits + row * ld, (size_t)n * row_bytes,
+                                cudaMemcpyHostToDevice, C.s_copy));
+        LA_CUDA(cudaEventRecord(C.ev_copied[sbuf], C.s_copy));
+        LA_CUDA(cudaStreamWaitEvent(C.s_comp, C.ev_copied[sbuf], 0));
+        rc = emit_rows(P, static_cast<const float*>(C.d_stage[sbuf]), ld, nullptr, 0, C.d_ws, row, n, C.s_comp);
         if (rc) return rc;
-        LA_CUDA(cudaEventRecord(P->ev_done[sbuf], P->s_comp));
+        LA_CUDA(cudaEventRecord(C.ev_done[sbuf], C.s_comp));
         used[sbuf] = true;
         row += n;
         ++i;
     }
-    int rc = la_viterbi(P, P->d_ws, d_first, d_last, d_score, d_status, P->s_comp);
+    rc = la_viterbi(P, C.d_ws, d_first, d_last, d_score, d_status, C.s_comp);
     if (rc) return rc;
+    // one D2H of the packed results into the pinned bounce buffer, then scatter on the host
+    LA_CUDA(cudaMemcpyAsync(C.h_out, C.d_out, out_bytes - 64, cudaMemcpyDeviceToHost, C.s_comp));
+    LA_CUDA(cudaStreamSynchronize(C.s_comp));
+    const unsigned char* h = static_cast<const unsigned char*>(C.h_out);
     if (P->total_L > 0) {
-        LA_CUDA(cudaMemcpyAsync(h_first, d_first, (size_t)P->total_L * 4, cudaMemcpyDeviceToHost, P->s_comp));
-        LA_CUDA(cudaMemcpyAsync(h_last, d_last, (size_t)P->total_L * 4, cudaMemcpyDeviceToHost, P->s_comp));
+        memcpy(h_first, h, (size_t)P->total_L * 4);
+        memcpy(h_last, h + lab_bytes, (size_t)P->total_L * 4);
     }
     if (P->n_utt > 0) {
-        LA_CUDA(cudaMemcpyAsync(h_score, d_score, (size_t)P->n_utt * 8, cudaMemcpyDeviceToHost, P->s_comp));
-        LA_CUDA(cudaMemcpyAsync(h_status, d_status, (size_t)P->n_utt * 4, cudaMemcpyDeviceToHost, P->s_comp));
+        memcpy(h_score, h + 2 * lab_bytes, (size_t)P->n_utt * 8);
+        memcpy(h_status, h + 2 * lab_bytes + sc_bytes, (size_t)P->n_utt * 4);
     }
-    LA_CUDA(cudaStreamSynchronize(P->s_comp));
     return LA_OK;
 }
 
