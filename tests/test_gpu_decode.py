@@ -20,7 +20,7 @@ def emission_tolerance(pred_row_sil, ctc):
     fp32 `log(1 - sigmoid(z))` carries by construction, ~2^-23 (1 + e^z) (the reference's own
     chain has it too; SURVEY.md section 7 hard part 4)."""
     z = pred_row_sil.astype(np.float64)
-    return 2e-5 + (2.0 ** -22 * (1.0 + np.exp(z)) if ctc else 0.0)
+    return 2e-5 + (2.0 ** -22 * (1.0 + np.exp(z)) if ctc else np.zeros_like(z))
 
 
 def run_plan(pred, rows, mode, t_len=None):
