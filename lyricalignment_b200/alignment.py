@@ -35,6 +35,9 @@ def _label_rows(labels) -> List[np.ndarray]:
     """utils/alignment.py:141: keep everything that is not the -100 padding."""
     if torch.is_tensor(labels):
         labels = labels.detach().cpu().numpy()
+    if isinstance(labels, np.ndarray) and labels.ndim == 2:
+        lab = labels.astype(np.int64, copy=False)
+        return [r[r != -100] for r in lab]
     rows = []
     for row in labels:
         r = np.asarray(row, dtype=np.int64).reshape(-1)
@@ -110,8 +113,14 @@ class AlignResult:
     l_len: np.ndarray        # int32 [B]
 
 
+_cuda_ok = None
+
+
 def _require_cuda():
-    if not torch.cuda.is_available():
+    global _cuda_ok
+    if _cuda_ok is None:
+        _cuda_ok = bool(torch.cuda.is_available())
+    if not _cuda_ok:
         raise _lib.LyricAlignError("lyricalignment_b200 needs a CUDA device (no CPU fallback)")
 
 

@@ -38,6 +38,7 @@ struct la_plan {
     int wide_warps[kBuckets] = {0, 0, 0, 0, 0};
     // device metadata blob
     void* d_meta = nullptr;
+    bool meta_pooled = false;
     la::BatchMeta meta{};
     const int32_t* d_order[kBuckets] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -58,6 +59,51 @@ struct HostCtx {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
 static HostCtx g_host[64];
+
+// Plan metadata lives in pooled 64 KiB device blocks: cudaMalloc / cudaFree (the latter a device-wide
+// sync) cost milliseconds next to a 40 MB clip, and the reference's entry points decode one clip
+// per call.
+constexpr size_t kMetaBlock = 64 << 10;
+struct DevInfo {
+    std::mutex mu;
+    int sm_count = 0;
+    std::vector<void*> free_blocks;
+};
+static DevInfo g_dev[64];
+
+static int meta_alloc(int device, size_t bytes, void** out, bool* pooled) {
+    DevInfo& D = g_dev[device];
+    if (bytes <= kMetaBlock) {
+        std::lock_guard<std::mutex> lock(D.mu);
+        *pooled = true;
+        if (!D.free_blocks.empty()) { *out = D.free_blocks.back(); D.free_blocks.pop_back(); return LA_OK; }
+        LA_CUDA(cudaMalloc(out, kMetaBlock));
+        return LA_OK;
+    }
+    *pooled = false;
+    LA_CUDA(cudaMalloc(out, bytes));
+    return LA_OK;
+}
+static void meta_free(int device, void* p, bool pooled) {
+    if (!p) return;
+    if (pooled) {
+        std::lock_guard<std::mutex> lock(g_dev[device].mu);
+        g_dev[device].free_blocks.push_back(p);
+    } else {
+        cudaFree(p);
+    }
+}
+static int device_sm_count(int device, int* out) {
+    DevInfo& D = g_dev[device];
+    std::lock_guard<std::mutex> lock(D.mu);
+    if (D.sm_count == 0) {
+        int n = 0;
+        LA_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+        D.sm_count = n;
+    }
+    *out = D.sm_count;
+    return LA_OK;
+}
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -130,12 +176,10 @@ int la_plan_create(la_plan** out, int mode, int n_utt, int V, const int32_t* h_t
     P->bp_bytes = align_up(bp_words * 4 + 16, 256);
 
     // device metadata blob
+    if (device < 0 || device >= 64) { delete P; return fail(LA_ERR_ARG, "device index out of range"); }
     cudaError_t ce = cudaSetDevice(device);
     if (ce != cudaSuccess) { delete P; return cuda_fail(ce, "cudaSetDevice"); }
-    cudaDeviceProp prop;
-    ce = cudaGetDeviceProperties(&prop, device);
-    if (ce != cudaSuccess) { delete P; return cuda_fail(ce, "cudaGetDeviceProperties"); }
-    P->sm_count = prop.multiProcessorCount;
+    if (int rc = device_sm_count(device, &P->sm_count)) { delete P; return rc; }
     std::vector<unsigned char> blob;
     auto put = [&](const void* src, size_t bytes) -> size_t {
         const size_t off = align_up(blob.size(), 16);
@@ -152,10 +196,9 @@ int la_plan_create(la_plan** out, int mode, int n_utt, int V, const int32_t* h_t
     const size_t o_bpp = put(P->bp_pairs.data(), P->bp_pairs.size() * 4);
     size_t o_ord[kBuckets];
     for (int b = 0; b < kBuckets; ++b) o_ord[b] = put(P->order[b].data(), P->order[b].size() * 4);
-    ce = cudaMalloc(&P->d_meta, blob.size());
-    if (ce != cudaSuccess) { delete P; return cuda_fail(ce, "cudaMalloc(meta)"); }
+    if (int rc = meta_alloc(device, blob.size(), &P->d_meta, &P->meta_pooled)) { delete P; return rc; }
     ce = cudaMemcpy(P->d_meta, blob.data(), blob.size(), cudaMemcpyHostToDevice);
-    if (ce != cudaSuccess) { cudaFree(P->d_meta); delete P; return cuda_fail(ce, "cudaMemcpy(meta)"); }
+    if (ce != cudaSuccess) { meta_free(device, P->d_meta, P->meta_pooled); delete P; return cuda_fail(ce, "cudaMemcpy(meta)"); }
     unsigned char* d = static_cast<unsigned char*>(P->d_meta);
     P->meta.n_utt = n_utt; P->meta.V = V; P->meta.mode = mode;
     P->meta.t_off = reinterpret_cast<const int32_t*>(d + o_t);
@@ -172,8 +215,7 @@ int la_plan_create(la_plan** out, int mode, int n_utt, int V, const int32_t* h_t
 
 void la_plan_destroy(la_plan* P) {
     if (!P) return;
-    cudaSetDevice(P->device);
-    if (P->d_meta) cudaFree(P->d_meta);
+    meta_free(P->device, P->d_meta, P->meta_pooled);
     delete P;
 }
 

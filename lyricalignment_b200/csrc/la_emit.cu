@@ -12,7 +12,8 @@
 //     (V is odd), so the copy covers the 16-byte-aligned interior and <= 3 tail floats are read
 //     directly;
 //   * 8 consumer warps pull float4s out of the ring, release the stage immediately, and keep a
-//     per-thread online (max, sum-exp) pair -- one pass over shared memory, 17 expf per 16 values;
+//     per-thread online (max, sum-exp) pair -- one pass over shared memory, FFMA + MUFU.EX2 + FADD
+//     per logit (the normaliser only; see ex2_approx);
 //   * per row: block reduce of the (max, sum) pairs, then L+1 threads gather the label / silence
 //     logits (L2-hot, the row has just streamed through) and apply the reference's exact
 //     formulas in fp32: (z - max) - log(sum); naive 1/(1+exp(-z)) sigmoid; log(1 - s); add;
@@ -51,6 +52,17 @@ __device__ __forceinline__ RowGeom row_geom(int64_t row, int64_t ld, int V) {
     g.ntail = (int)((re - g.tail_start) >> 2);
     return g;
 }
+
+// 2^x on the SFU (MUFU.EX2, max rel. error 2^-22). Used ONLY for the sum-exp normaliser, where
+// 21127 terms are accumulated and the result goes through a log: the LSE moves by < 3e-7, far
+// below the ulp-level differences between libm/Sleef/CUDA expf that the reference's own chain
+// already has. The label-column epilogue keeps the exact fp32 formulas with full-precision libm.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
 
 template <int MODE>
 __global__ void __launch_bounds__(kEmitThreads, 2) emit_kernel(const EmitParams p) {
@@ -159,13 +171,14 @@ __global__ void __launch_bounds__(kEmitThreads, 2) emit_kernel(const EmitParams 
             }
             if (mx > -INFINITY) {
                 const float mn = fmaxf(m, mx);
-                float acc = s * expf(m - mn);
+                const float mn2 = mn * kLog2e;
+                float acc = s * ex2_approx((m - mn) * kLog2e);
 #pragma unroll
-                for (int k = 0; k < kF4PerThread; ++k) {
-                    acc += expf(v[k].x - mn);
-                    acc += expf(v[k].y - mn);
-                    acc += expf(v[k].z - mn);
-                    acc += expf(v[k].w - mn);
+                for (int k = 0; k < kF4PerThread; ++k) {      // 1 FFMA + 1 MUFU + 1 FADD per logit
+                    acc += ex2_approx(fmaf(v[k].x, kLog2e, -mn2));
+                    acc += ex2_approx(fmaf(v[k].y, kLog2e, -mn2));
+                    acc += ex2_approx(fmaf(v[k].z, kLog2e, -mn2));
+                    acc += ex2_approx(fmaf(v[k].w, kLog2e, -mn2));
                 }
                 s = acc;
                 m = mn;
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(kEmitThreads, 2) emit_kernel(const EmitParams 
             if (col >= lo && col <= hi) {
                 const float x = __ldg(reinterpret_cast<const float*>(gbase + g.tail_start) + tid);
                 const float mn = fmaxf(m, x);
-                s = s * expf(m - mn) + expf(x - mn);
+                s = s * ex2_approx((m - mn) * kLog2e) + ex2_approx((x - mn) * kLog2e);
                 m = mn;
             }
         }
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(kEmitThreads, 2) emit_kernel(const EmitParams 
         float wm = m;
 #pragma unroll
         for (int o = 16; o; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-        float ws = (m > -INFINITY) ? s * expf(m - wm) : 0.f;
+        float ws = (m > -INFINITY) ? s * ex2_approx((m - wm) * kLog2e) : 0.f;
 #pragma unroll
         for (int o = 16; o; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
         float2* rr = red + (row & 1) * (kEmitConsumers / 32);
@@ -203,7 +216,7 @@ __global__ void __launch_bounds__(kEmitThreads, 2) emit_kernel(const EmitParams 
 #pragma unroll
         for (int w = 0; w < kEmitConsumers / 32; ++w) {
             const float2 q = rr[w];
-            S += (q.x > -INFINITY) ? q.y * expf(q.x - M) : 0.f;
+            S += (q.x > -INFINITY) ? q.y * ex2_approx((q.x - M) * kLog2e) : 0.f;
         }
         const float logS = logf(S);
 

@@ -219,8 +219,11 @@ def test_host_path_streams_in_several_stages():
     dev = A._run_device(plan, pred.cuda())
     host = A._run_host(plan, pred.pin_memory(), staging_bytes=37 * V * 4)   # 37 rows per stage: splits utterances
     plan.close()
-    for f in ("first", "last_plus1", "score", "status"):
+    for f in ("first", "last_plus1", "status"):
         assert np.array_equal(getattr(dev, f), getattr(host, f)), f
+    # staging re-bases the rows, which changes the 16-byte phase of each row and with it the
+    # fp32 summation order of the normaliser: scores agree to fp32 rounding, not bitwise
+    np.testing.assert_allclose(dev.score, host.score, rtol=1e-6)
 
 
 def test_strided_and_misaligned_input():
