@@ -127,14 +127,24 @@ int la_align_host(la_plan* plan, const float* h_logits, int64_t ld, int32_t* h_f
 
 /* ---- K1: log-mel front end --------------------------------------------------------------
  * Replaces whisper.audio.log_mel_spectrogram as called at module/align_model.py:84:
- * d_wave float32 [B][n_samples] (zero-padded to the batch maximum, align_model.py:78-82)
- * -> d_out float32 [B][80][out_stride] with the first n_samples/160 frames of every row
- * written (frames beyond that are left untouched, so the caller can pre-zero a 3000-frame
- * encoder window, align_model.py:89). The max-8 floor uses the GLOBAL maximum over the call.
- * Workspace: la_logmel_workspace_bytes(B, n_samples). */
-size_t la_logmel_workspace_bytes(int batch, int64_t n_samples);
-int la_logmel(const float* d_wave, int batch, int64_t n_samples, int64_t wave_stride,
-              float* d_out, int64_t out_stride, void* d_workspace, void* stream);
+ * d_wave float32 [batch][n_samples] (row stride wave_stride floats; the reference zero-pads every
+ * clip to the batch maximum, align_model.py:78-82) -> d_out float32 [batch][80][out_stride] with
+ * the first n_samples/160 frames of every mel row written (columns beyond that are left
+ * untouched, so the caller can pre-zero a 3000-frame encoder window, align_model.py:89). The
+ * max-8 floor uses the GLOBAL maximum over the whole call, as whisper does. d_wave must be
+ * 16-byte aligned; n_samples > 200 (reflect padding).
+ * Workspace: la_logmel_workspace_bytes(n_clips, total_samples) bytes of device memory. */
+size_t la_logmel_workspace_bytes(int n_clips, int64_t total_samples);
+int la_logmel(const float* d_wave, int batch, int64_t n_samples, int64_t wave_stride, float* d_out,
+              int64_t out_stride, void* d_workspace, void* stream);
+
+/* Ragged form: n_clips INDEPENDENT calls of the above with batch 1 (the reference's default
+ * --batch-size 1: every clip gets its own maximum) in one launch. Clip c reads
+ * d_wave[h_wave_off[c] .. + h_n_samples[c]) and writes d_out[h_out_off[c] + m*h_out_stride[c] + f].
+ * Offsets that are multiples of 4 floats take the TMA path. The h_* arrays are host memory. */
+int la_logmel_ragged(const float* d_wave, int n_clips, const int64_t* h_wave_off,
+                     const int32_t* h_n_samples, float* d_out, const int64_t* h_out_off,
+                     const int32_t* h_out_stride, void* d_workspace, void* stream);
 
 #ifdef __cplusplus
 }

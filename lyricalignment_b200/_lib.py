@@ -34,6 +34,7 @@ SIGNATURES = {
     "la_align_host": (_c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz]),
     "la_logmel_workspace_bytes": (_sz, [_c_int, _i64]),
     "la_logmel": (_c_int, [_vp, _c_int, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "la_logmel_ragged": (_c_int, [_vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

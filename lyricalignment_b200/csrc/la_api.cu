@@ -25,6 +25,10 @@ static int cuda_fail(cudaError_t e, const char* where) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #x);    \
     } while (0)
 
+namespace la {
+int set_error(int code, const char* msg) { return fail(code, msg); }
+}
+
 constexpr int kBuckets = 5;
 
 struct la_plan {

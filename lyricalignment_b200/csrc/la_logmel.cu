@@ -1,6 +1,573 @@
-// la_logmel.cu -- K1 placeholder until the tcgen05 front end lands.
+// la_logmel.cu -- K1: Whisper-style 80-bin log-mel front end as a framed, windowed DFT on the
+// 5th-gen tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, fp32 accumulators in TMEM).
+//
+// Replaces whisper.audio.log_mel_spectrogram as called at module/align_model.py:84 (the
+// reference runs it on the CPU through torch.stft): hann(400, periodic) window, hop 160,
+// centre=True reflect padding, last frame dropped, |.|^2, 80 x 201 Slaney mel filterbank,
+// log10(clamp 1e-10), max(x, GLOBAL max - 8), (x + 4) / 4.
+//
+// Formulation. The Hann window is symmetric (w[n] = w[400-n], w[0] = 0), so with the folded
+// inputs  e[n] = x[n] + x[400-n],  o[n] = x[n] - x[400-n]  (n = 1..199; e[200] = x[200]):
+//     Re X[k] = sum_{n=1..200} e[n] * w[n] cos(2 pi k n / 400)
+//     Im X[k] = sum_{n=1..199} o[n] * (-w[n] sin(2 pi k n / 400))
+// i.e. two GEMMs [128 frames x 200] x [200 x 208] per tile -- half the FLOPs and half the basis
+// bytes of the plain [128 x 400] x [400 x 402] product. Precision: every operand is split
+// x = hi + lo with hi exactly representable in TF32; the kernel issues hi*hi + hi*lo + lo*hi
+// (the dropped lo*lo term is 2^-22 relative), which lands 1e-6..1e-5 from the fp64 oracle in
+// the log10 domain (single-pass TF32 would be 3e-1 off on tonal input).
+//
+// One persistent CTA per SM, 128-frame tiles, warp-specialised:
+//   warp 0      producer: 1-D TMA bulk copies of the tile's waveform rows (130 hop rows of 640 B
+//               into a 656 B-pitch, bank-conflict-free staging area) and of the constant basis
+//               blocks (13 KB per half k-step, L2-resident) into a 6-deep ring;
+//   warp 1      TMEM allocator + MMA issuer (one elected lane, 150 tcgen05.mma per tile);
+//   warps 4..7  transform: staged waveform -> folded, hi/lo-split A operand in the UMMA
+//               canonical no-swizzle K-major layout (bank-conflict-free both ways); then, per
+//               tile, the epilogue: TMEM -> registers, power, sparse mel projection (each FFT
+//               bin feeds <= 2 adjacent triangular filters), log10 clamp, coalesced stores and
+//               the running maximum.
+// Clip-boundary tiles (reflect padding, ragged ends) are staged by the transform warps with
+// plain loads instead of TMA. A second tiny kernel applies the max-8 floor and (x+4)/4.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
 #include "../../include/lyricalign.h"
-extern "C" {
-size_t la_logmel_workspace_bytes(int, int64_t) { return 0; }
-int la_logmel(const float*, int, int64_t, int64_t, float*, int64_t, void*, void*) { return LA_ERR_ARG; }
+#include "la_common.cuh"
+
+namespace la {
+
+constexpr int kNfft = 400, kHop = 160, kMels = 80, kBins = 201;
+constexpr int kTileM = 128;                 // frames per tile
+constexpr int kNpad = 208;                  // 201 bins padded to a multiple of 16
+constexpr int kKSteps = 25;                 // 200 folded samples / 8 (UMMA_K for tf32)
+constexpr int kRawRows = 130;               // hop rows staged per tile
+constexpr int kRawPitch = 164;              // floats; 8 rows x 4 cols hit 32 distinct banks
+constexpr int kALbo = 2064;                 // bytes between K-adjacent core matrices of A (16 * 128 + 16 pad)
+constexpr int kABytes = 2 * kALbo;          // one A operand (hi or lo) of one k-step
+constexpr int kBLbo = (kNpad / 8) * 128;    // 3328
+constexpr int kBBytes = 2 * kBLbo;          // 6656: one B operand (hi or lo) of one k-step
+constexpr int kStageBytes = 21632;          // 2*kABytes + 2*kBBytes = 21568, padded to 128
+constexpr int kStages = 6;
+constexpr int kRawBytes = kRawRows * kRawPitch * 4;   // 85280
+constexpr int kLogmelThreads = 256;
+constexpr uint32_t kTmemCols = 512;
+
+struct ClipDesc {
+    int64_t wave_off;   // float offset of the clip's first sample
+    int64_t out_off;    // float offset of out[clip][0][0]
+    int32_t n_samples;
+    int32_t n_frames;
+    int32_t out_stride; // floats between mel rows
+    int32_t group;      // clips of one group share the max-8 floor (one whisper call)
+    int32_t tile0;      // first tile of the clip
+    int32_t pad;
+};
+
+struct LogmelParams {
+    const float* wave;
+    float* out;
+    const ClipDesc* clips;
+    const int32_t* tile_clip;     // [n_tiles]
+    int n_tiles;
+    int n_clips;
+    const float* basis;           // [25][even: C_hi, C_lo | odd: S_hi, S_lo] canonical UMMA layout
+    int* group_max;               // ordered-int encoded running maxima
+};
+
+__constant__ float c_mel_w0[kBins];
+__constant__ float c_mel_w1[kBins];
+__constant__ int c_mel_lo[kBins];
+
+// ---- tcgen05 wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start>>4 at
+// [0,14), leading (K-direction core-matrix) byte offset>>4 at [16,30), stride (M/N-direction)
+// byte offset>>4 at [32,46), version 1 at [46,48), layout type 0 at [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor: D = f32 (1 @ [4,6)), A = B = tf32 (2 @ [7,10), [10,13)), both
+// K-major, N>>3 @ [17,23), M>>4 @ [24,29).
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNpad >> 3) << 17) |
+                            ((uint32_t)(kTileM >> 4) << 24);
+
+__device__ __forceinline__ int float_to_ordered(float v) {
+    const int i = __float_as_int(v);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int k) {
+    return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+
+__global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* stages = smem;
+    float* raw = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kRawBytes);
+    uint64_t* full = bars;                    // [kStages] B landed (tx) + 4 transform warps
+    uint64_t* empty = bars + kStages;         // [kStages] MMAs of the stage retired
+    uint64_t* raw_full = bars + 2 * kStages;
+    uint64_t* raw_empty = raw_full + 1;
+    uint64_t* tmem_full = raw_full + 2;
+    uint64_t* tmem_empty = raw_full + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_full + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 5); mbar_init(&empty[s], 1); }
+        mbar_init(raw_full, 1);
+        mbar_init(raw_empty, 4);
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== producer ==========================================
+        if (lane == 0) {
+            uint32_t it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
+                const ClipDesc c = p.clips[p.tile_clip[tile]];
+                const int f0 = (tile - c.tile0) * kTileM;
+                const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
+                const bool interior = j0 >= 0 && j0 + kRawRows * kHop <= c.n_samples && (c.wave_off & 3) == 0;
+                mbar_wait(raw_empty, (tl & 1) ^ 1);
+                if (interior) {
+                    mbar_arrive_expect_tx(raw_full, kRawRows * kHop * 4);
+                    const float* src = p.wave + c.wave_off + j0;
+                    for (int h = 0; h < kRawRows; ++h)
+                        bulk_g2s(raw + h * kRawPitch, src + h * kHop, kHop * 4, raw_full);
+                } else {
+                    mbar_arrive(raw_full);             // the transform warps stage boundary tiles themselves
+                }
+                for (int hs = 0; hs < 2 * kKSteps; ++hs, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full[s], 2 * kBBytes);
+                    bulk_g2s(stages + s * kStageBytes + 2 * kABytes,
+                             reinterpret_cast<const unsigned char*>(p.basis) + (size_t)hs * 2 * kBBytes, 2 * kBBytes,
+                             &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ========================================
+        if (lane == 0) {
+            uint32_t it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
+                mbar_wait(tmem_empty, (tl & 1) ^ 1);       // epilogue of the previous tile drained TMEM
+                tc_fence_after();
+                for (int hs = 0; hs < 2 * kKSteps; ++hs, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(&full[s], (it / kStages) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stages + s * kStageBytes);
+                    const uint64_t a_hi = umma_desc(sa, kALbo, 128);
+                    const uint64_t a_lo = umma_desc(sa + kABytes, kALbo, 128);
+                    const uint64_t b_hi = umma_desc(sa + 2 * kABytes, kBLbo, 128);
+                    const uint64_t b_lo = umma_desc(sa + 2 * kABytes + kBBytes, kBLbo, 128);
+                    const uint32_t d = tmem_base + ((hs & 1) ? kNpad : 0);   // even -> Re, odd -> Im
+                    umma_tf32(d, a_hi, b_lo, kIdesc, hs >= 2 ? 1u : 0u);      // small terms first
+                    umma_tf32(d, a_lo, b_hi, kIdesc, 1u);
+                    umma_tf32(d, a_hi, b_hi, kIdesc, 1u);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(tmem_full);
+            }
+        }
+    } else if (warp >= 4) {
+        // ====================== transform + epilogue (128 threads) ==========================
+        const int wq = warp - 4;                   // TMEM lane quarter == warp % 4
+        const int row = wq * 32 + lane;            // frame row of this thread in the epilogue
+        const int et = tid - 128;
+        uint32_t it = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
+            const ClipDesc c = p.clips[p.tile_clip[tile]];
+            const int f0 = (tile - c.tile0) * kTileM;
+            const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
+            const bool interior = j0 >= 0 && j0 + kRawRows * kHop <= c.n_samples && (c.wave_off & 3) == 0;
+            mbar_wait(raw_full, tl & 1);
+            if (!interior) {
+                // reflect padding (torch.stft centre=True) and ragged clip ends, by plain loads
+                const float* x = p.wave + c.wave_off;
+                const int N = c.n_samples;
+                for (int idx = et; idx < kRawRows * kHop; idx += 128) {
+                    int64_t j = j0 + idx;
+                    if (j < 0) j = -j;
+                    if (j >= N) j = 2 * (int64_t)(N - 1) - j;
+                    j = j < 0 ? 0 : (j >= N ? N - 1 : j);
+                    raw[(idx / kHop) * kRawPitch + idx % kHop] = __ldg(x + j);
+                }
+                named_bar_sync(2, 128);
+            }
+            // ---- A operand: fold + hi/lo split, 50 half k-steps -----------------------------
+            const int rsub = lane >> 2, kq = lane & 3;
+            for (int hs = 0; hs < 2 * kKSteps; ++hs, ++it) {
+                const int s = it % kStages;
+                mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                unsigned char* st = stages + s * kStageBytes;
+                const int kstep = hs >> 1;
+                const bool odd = hs & 1;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int r = wq * 32 + g * 8 + rsub;
+#pragma unroll
+                    for (int ki = 0; ki < 2; ++ki) {
+                        const int n = kstep * 8 + ki * 4 + kq + 1;           // 1..200
+                        const int sf = r * kHop + n, sr = r * kHop + kNfft - n;
+                        const float fwd = raw[(sf / kHop) * kRawPitch + sf % kHop];
+                        const float rev = raw[(sr / kHop) * kRawPitch + sr % kHop];
+                        float v;
+                        if (n == kNfft / 2) v = odd ? 0.f : fwd;
+                        else v = odd ? fwd - rev : fwd + rev;
+                        const float hi = __int_as_float(__float_as_int(v) & 0xffffe000);
+                        const float lo = v - hi;
+                        const int off = ki * kALbo + (r >> 3) * 128 + (r & 7) * 16 + kq * 4;
+                        *reinterpret_cast<float*>(st + off) = hi;
+                        *reinterpret_cast<float*>(st + kABytes + off) = lo;
+                    }
+                }
+                fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(raw_empty);      // staged waveform no longer needed
+
+            // ---- epilogue: power -> mel -> log10, straight out of TMEM ------------------------
+            mbar_wait(tmem_full, tl & 1);
+            tc_fence_after();
+            const int f = f0 + row;
+            const bool valid = f < c.n_frames;
+            float* outp = p.out + c.out_off + f;
+            float mx = -INFINITY;
+            int cur = 0;
+            float a0 = 0.f, a1 = 0.f;
+            auto emit = [&](int m, float v) {
+                const float lg = log10f(fmaxf(v, 1e-10f));
+                if (valid && m < kMels) {
+                    outp[(int64_t)m * c.out_stride] = lg;
+                    mx = fmaxf(mx, lg);
+                }
+            };
+            const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+            for (int cb = 0; cb < kNpad; cb += 16) {
+                uint32_t re[16], im[16];
+                tmem_ld16(lane_base + cb, re);
+                tmem_ld16(lane_base + kNpad + cb, im);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int k = cb + q;
+                    if (k < kBins) {
+                        const float xr = __uint_as_float(re[q]), xi = __uint_as_float(im[q]);
+                        const float pw = xr * xr + xi * xi;
+                        const int ml = c_mel_lo[k];
+                        while (cur < ml) { emit(cur, a0); a0 = a1; a1 = 0.f; ++cur; }
+                        a0 = fmaf(c_mel_w0[k], pw, a0);
+                        a1 = fmaf(c_mel_w1[k], pw, a1);
+                    }
+                }
+            }
+            while (cur < kMels) { emit(cur, a0); a0 = a1; a1 = 0.f; ++cur; }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0 && mx > -INFINITY) atomicMax(p.group_max + c.group, float_to_ordered(mx));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// out = (max(x, gmax - 8) + 4) / 4 over the valid frames of every clip
+__global__ void logmel_finalize_kernel(const LogmelParams p) {
+    const ClipDesc c = p.clips[blockIdx.y];
+    const float floor_v = ordered_to_float(p.group_max[c.group]) - 8.0f;
+    const int total = kMels * c.n_frames;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int m = i / c.n_frames, f = i - m * c.n_frames;
+        float* q = p.out + c.out_off + (int64_t)m * c.out_stride + f;
+        *q = (fmaxf(*q, floor_v) + 4.0f) / 4.0f;
+    }
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---- host: constant tables ---------------------------------------------------------------
+static void tf32_split(double v, float* hi, float* lo) {
+    float f = (float)v;
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u = (u + 0x1000u) & 0xffffe000u;          // round to nearest TF32 (10 explicit mantissa bits)
+    float h;
+    memcpy(&h, &u, 4);
+    *hi = h;
+    *lo = (float)(v - (double)h);
+}
+
+// librosa.filters.mel(sr=16000, n_fft=400, n_mels=80): Slaney scale + Slaney area norm, fp32 out
+static void build_mel(std::vector<float>& W) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    auto hz_to_mel = [&](double f) { return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp; };
+    auto mel_to_hz = [&](double m) { return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m; };
+    const double mmax = hz_to_mel(8000.0);
+    std::vector<double> mel_f(kMels + 2);
+    for (int i = 0; i < kMels + 2; ++i) {
+        const double m = (i == kMels + 1) ? mmax : i * (mmax / (kMels + 1));
+        mel_f[i] = mel_to_hz(m);
+    }
+    W.assign((size_t)kMels * kBins, 0.f);
+    for (int i = 0; i < kMels; ++i) {
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        for (int k = 0; k < kBins; ++k) {
+            const double fr = 8000.0 * k / (kBins - 1);
+            const double lower = -(mel_f[i] - fr) / (mel_f[i + 1] - mel_f[i]);
+            const double upper = (mel_f[i + 2] - fr) / (mel_f[i + 2] - mel_f[i + 1]);
+            const float w = (float)std::max(0.0, std::min(lower, upper));
+            W[(size_t)i * kBins + k] = (float)((double)w * enorm);
+        }
+    }
+}
+
+struct LogmelTables {
+    std::mutex mu;
+    float* d_basis[64] = {nullptr};
+    bool const_done[64] = {false};
+};
+static LogmelTables g_tab;
+
+static cudaError_t ensure_tables(int device, const float** basis_out) {
+    std::lock_guard<std::mutex> lock(g_tab.mu);
+    if (!g_tab.d_basis[device]) {
+        // basis blocks: per k-step j: [C_hi | C_lo] (even half-step) then [S_hi | S_lo] (odd), each
+        // matrix in the canonical K-major layout [ki 2][ni 26][8 rows (bin)][4 floats (sample)]
+        std::vector<float> h((size_t)kKSteps * 4 * (kBBytes / 4), 0.f);
+        const double PI = 3.14159265358979323846;
+        for (int j = 0; j < kKSteps; ++j)
+            for (int kk = 0; kk < 8; ++kk) {
+                const int n = j * 8 + kk + 1;                               // 1..200
+                const double w = 0.5 - 0.5 * std::cos(2.0 * PI * n / kNfft);
+                for (int b = 0; b < kNpad; ++b) {
+                    double cv = 0.0, sv = 0.0;
+                    if (b < kBins) {
+                        const int ph = (int)(((long long)b * n) % kNfft);     // exact phase reduction
+                        cv = w * std::cos(2.0 * PI * ph / kNfft);
+                        sv = (n == kNfft / 2) ? 0.0 : -w * std::sin(2.0 * PI * ph / kNfft);
+                    }
+                    const size_t inner = (size_t)(kk >> 2) * (kBLbo / 4) + (size_t)(b >> 3) * 32 + (b & 7) * 4 + (kk & 3);
+                    const size_t base = (size_t)j * 4 * (kBBytes / 4);
+                    tf32_split(cv, &h[base + inner], &h[base + (kBBytes / 4) + inner]);
+                    tf32_split(sv, &h[base + 2 * (kBBytes / 4) + inner], &h[base + 3 * (kBBytes / 4) + inner]);
+                }
+            }
+        float* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, h.size() * 4);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(d); return e; }
+        g_tab.d_basis[device] = d;
+    }
+    if (!g_tab.const_done[device]) {
+        std::vector<float> W;
+        build_mel(W);
+        float w0[kBins], w1[kBins];
+        int lo[kBins];
+        int prev = 0;
+        for (int k = 0; k < kBins; ++k) {
+            int first = -1;
+            for (int m = 0; m < kMels; ++m)
+                if (W[(size_t)m * kBins + k] != 0.f) { first = m; break; }
+            if (first < 0) { lo[k] = prev; w0[k] = 0.f; w1[k] = 0.f; continue; }
+            lo[k] = first;
+            w0[k] = W[(size_t)first * kBins + k];
+            w1[k] = first + 1 < kMels ? W[(size_t)(first + 1) * kBins + k] : 0.f;
+            prev = first;
+        }
+        cudaError_t e = cudaMemcpyToSymbol(c_mel_w0, w0, sizeof(w0));
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyToSymbol(c_mel_w1, w1, sizeof(w1));
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyToSymbol(c_mel_lo, lo, sizeof(lo));
+        if (e != cudaSuccess) return e;
+        g_tab.const_done[device] = true;
+    }
+    *basis_out = g_tab.d_basis[device];
+    return cudaSuccess;
+}
+
+size_t logmel_smem_bytes() { return (size_t)kStages * kStageBytes + kRawBytes + 256; }
+
+}  // namespace la
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_lm_err[256];   // scratch for formatting; the message is handed to la::set_error
+#define LM_FAIL(code) return la::set_error(code, g_lm_err)
+
+static inline size_t lm_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int logmel_run(const float* d_wave, float* d_out, const std::vector<la::ClipDesc>& clips_in, int n_groups,
+                      void* d_ws, size_t ws_bytes, cudaStream_t stream) {
+    using namespace la;
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "cudaGetDevice: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
+    const float* basis = nullptr;
+    e = ensure_tables(device, &basis);
+    if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "tables: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
+    std::vector<ClipDesc> clips = clips_in;
+    std::vector<int32_t> tile_clip;
+    int max_frames = 0;
+    for (size_t ci = 0; ci < clips.size(); ++ci) {
+        clips[ci].tile0 = (int32_t)tile_clip.size();
+        const int nt = (clips[ci].n_frames + kTileM - 1) / kTileM;
+        for (int t = 0; t < nt; ++t) tile_clip.push_back((int32_t)ci);
+        max_frames = std::max(max_frames, clips[ci].n_frames);
+    }
+    const int n_tiles = (int)tile_clip.size();
+    if (n_tiles == 0) return LA_OK;
+    const size_t o_clips = 0;
+    const size_t o_tiles = lm_align(o_clips + clips.size() * sizeof(ClipDesc), 256);
+    const size_t o_max = lm_align(o_tiles + tile_clip.size() * 4, 256);
+    const size_t need = o_max + lm_align((size_t)n_groups * 4, 256);
+    if (ws_bytes < need) { snprintf(g_lm_err, sizeof g_lm_err, "workspace too small"); LM_FAIL(LA_ERR_ARG); }
+    unsigned char* ws = static_cast<unsigned char*>(d_ws);
+    e = cudaMemcpyAsync(ws + o_clips, clips.data(), clips.size() * sizeof(ClipDesc), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + o_tiles, tile_clip.data(), tile_clip.size() * 4, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "meta upload: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
+    // pageable sources: the copies above complete (w.r.t. the host buffers) before returning
+    LogmelParams p;
+    p.wave = d_wave; p.out = d_out;
+    p.clips = reinterpret_cast<const ClipDesc*>(ws + o_clips);
+    p.tile_clip = reinterpret_cast<const int32_t*>(ws + o_tiles);
+    p.n_tiles = n_tiles; p.n_clips = (int)clips.size();
+    p.basis = basis;
+    p.group_max = reinterpret_cast<int*>(ws + o_max);
+    fill_int_kernel<<<(n_groups + 255) / 256, 256, 0, stream>>>(p.group_max, n_groups, INT32_MIN);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t smem = logmel_smem_bytes();
+    e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "smem attr: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
+    logmel_kernel<<<std::min(n_tiles, sms), kLogmelThreads, smem, stream>>>(p);
+    const int fx = std::max(1, std::min(64, (kMels * max_frames + 255) / 256));
+    logmel_finalize_kernel<<<dim3(fx, (unsigned)clips.size()), 256, 0, stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "launch: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
+    return LA_OK;
+}
+
+extern "C" {
+
+size_t la_logmel_workspace_bytes(int n_clips, int64_t total_samples) {
+    if (n_clips < 0 || total_samples < 0) return 0;
+    const size_t tiles = (size_t)(total_samples / la::kHop) / la::kTileM + (size_t)n_clips + 1;
+    return lm_align((size_t)n_clips * sizeof(la::ClipDesc), 256) + lm_align(tiles * 4, 256) +
+           lm_align((size_t)std::max(n_clips, 1) * 4, 256) + 256;
+}
+
+int la_logmel(const float* d_wave, int batch, int64_t n_samples, int64_t wave_stride, float* d_out,
+              int64_t out_stride, void* d_ws, void* stream) {
+    if (!d_wave || !d_out || !d_ws || batch < 0) { snprintf(g_lm_err, sizeof g_lm_err, "null argument"); LM_FAIL(LA_ERR_ARG); }
+    if (reinterpret_cast<uintptr_t>(d_wave) & 15) { snprintf(g_lm_err, sizeof g_lm_err, "waveform base must be 16-byte aligned"); LM_FAIL(LA_ERR_ARG); }
+    if (n_samples <= la::kNfft / 2) { snprintf(g_lm_err, sizeof g_lm_err, "reflect padding needs more than 200 samples"); LM_FAIL(LA_ERR_ARG); }
+    const int64_t F = n_samples / la::kHop;
+    if (out_stride < F || n_samples > INT32_MAX) { snprintf(g_lm_err, sizeof g_lm_err, "bad stride/size"); LM_FAIL(LA_ERR_ARG); }
+    std::vector<la::ClipDesc> clips((size_t)batch);
+    for (int b = 0; b < batch; ++b) {
+        clips[b].wave_off = (int64_t)b * wave_stride;
+        clips[b].out_off = (int64_t)b * la::kMels * out_stride;
+        clips[b].n_samples = (int32_t)n_samples;
+        clips[b].n_frames = (int32_t)F;
+        clips[b].out_stride = (int32_t)out_stride;
+        clips[b].group = 0;                       // one call == one global maximum (whisper semantics)
+        clips[b].tile0 = 0; clips[b].pad = 0;
+    }
+    return logmel_run(d_wave, d_out, clips, 1, d_ws, la_logmel_workspace_bytes(batch, (int64_t)batch * n_samples),
+                      static_cast<cudaStream_t>(stream));
+}
+
+int la_logmel_ragged(const float* d_wave, int n_clips, const int64_t* h_wave_off, const int32_t* h_n_samples,
+                     float* d_out, const int64_t* h_out_off, const int32_t* h_out_stride, void* d_ws, void* stream) {
+    if (!d_wave || !d_out || !d_ws || n_clips < 0 || !h_wave_off || !h_n_samples || !h_out_off || !h_out_stride) {
+        snprintf(g_lm_err, sizeof g_lm_err, "null argument");
+        LM_FAIL(LA_ERR_ARG);
+    }
+    if (reinterpret_cast<uintptr_t>(d_wave) & 15) { snprintf(g_lm_err, sizeof g_lm_err, "waveform base must be 16-byte aligned"); LM_FAIL(LA_ERR_ARG); }
+    std::vector<la::ClipDesc> clips((size_t)n_clips);
+    int64_t total = 0;
+    for (int c = 0; c < n_clips; ++c) {
+        if (h_n_samples[c] <= la::kNfft / 2) { snprintf(g_lm_err, sizeof g_lm_err, "clip %d too short for reflect padding", c); LM_FAIL(LA_ERR_ARG); }
+        clips[c].wave_off = h_wave_off[c];
+        clips[c].out_off = h_out_off[c];
+        clips[c].n_samples = h_n_samples[c];
+        clips[c].n_frames = h_n_samples[c] / la::kHop;
+        clips[c].out_stride = h_out_stride[c];
+        clips[c].group = c;                       // independent calls: one maximum per clip (batch size 1)
+        clips[c].tile0 = 0; clips[c].pad = 0;
+        if (clips[c].out_stride < clips[c].n_frames) { snprintf(g_lm_err, sizeof g_lm_err, "clip %d: out_stride < frames", c); LM_FAIL(LA_ERR_ARG); }
+        total += h_n_samples[c];
+    }
+    return logmel_run(d_wave, d_out, clips, std::max(n_clips, 1), d_ws, la_logmel_workspace_bytes(n_clips, total),
+                      static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
