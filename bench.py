@@ -6,7 +6,9 @@
 Workload (BASELINE.json configs[1]): an Opencpop-test-shaped batch of 2,000 synthetic clips of
 5-15 s, head width V = 21129 (fp32 logits, 84.5 KB per 20 ms frame), CTC-flavour decode
 (perform_viterbi_ctc) against 2.4 char/s pinyin-class lyrics. One "step" = one pass of the hot
-path (K2 fused log-softmax + gather, K3 Viterbi + backtrace) over the whole batch.
+path (K1 tcgen05 log-mel of every clip's waveform, K2 fused log-softmax + gather over the head
+logits, K3 Viterbi + backtrace) over the whole batch. The Whisper encoder + GRU head between K1
+and K2 are stock PyTorch and outside the product, so the logits are synthetic and resident.
 
   value  : whole-job audio-s/s with the logits resident in HBM (84.5 GB per GPU, >> L2, so every
            step streams from HBM); CUDA-event timed, max over ranks.
@@ -60,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -123,13 +125,16 @@ def cpu_decode_fn():
     return port, "port"
 
 
-def time_cpu(pool_pred, pool_labels, pool_dur, n_clips, repeats):
+def time_cpu(pool_pred, pool_labels, pool_dur, n_clips, repeats, pool_wave=None):
+    from oracle.logmel import log_mel_spectrogram_torch_f32
     fn, kind = cpu_decode_fn()
     fn(pool_pred[0][:, :8], [pool_labels[0][:1].tolist()])            # warm numba / libs
     times = []
     for _ in range(repeats):
         t0 = time.perf_counter()
         for i in range(n_clips):
+            if pool_wave is not None:
+                log_mel_spectrogram_torch_f32(pool_wave[i])           # whisper's CPU formulation
             fn(pool_pred[i], [pool_labels[i].tolist()])
         times.append(time.perf_counter() - t0)
     secs = float(sum(pool_dur[:n_clips]))
@@ -163,7 +168,7 @@ def main():
         return
 
     import torch.distributed as dist
-    from lyricalignment_b200 import _lib, alignment as A, sharded
+    from lyricalignment_b200 import _lib, alignment as A, audio as LA, sharded
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -184,8 +189,21 @@ def main():
     score = torch.empty(plan.n_utt, dtype=torch.float64, device=dev)
     status = torch.empty(plan.n_utt, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
+    # K1 inputs/outputs: ragged waveforms -> per-clip [80][F] log-mel (each clip its own call/max)
+    wave, w_off = synth.synthetic_waveforms(batch, device=dev, seed=114514 + rank)
+    n_samp = batch.n_samples.astype(np.int32)
+    mel_frames = (n_samp // 160).astype(np.int32)
+    mel_off = np.concatenate([[0], np.cumsum(80 * mel_frames.astype(np.int64))[:-1]]).astype(np.int64)
+    mel_out = torch.empty(int(80 * mel_frames.astype(np.int64).sum()), dtype=torch.float32, device=dev)
+    mel_ws = torch.empty(int(lib.la_logmel_workspace_bytes(len(n_samp), int(n_samp.astype(np.int64).sum()))),
+                         dtype=torch.uint8, device=dev)
 
-    def step(ev_a=None, ev_b=None):
+    def step(ev_m=None, ev_a=None, ev_b=None):
+        if ev_m is not None:
+            ev_m.record()
+        _lib.check(lib.la_logmel_ragged(wave.data_ptr(), len(n_samp), w_off.ctypes.data, n_samp.ctypes.data,
+                                        mel_out.data_ptr(), mel_off.ctypes.data, mel_frames.ctypes.data,
+                                        mel_ws.data_ptr(), stream), "la_logmel_ragged")
         if ev_a is not None:
             ev_a.record()
         _lib.check(lib.la_emit(plan.handle, logits.data_ptr(), V, None, 0, ws.data_ptr(), stream), "la_emit")
@@ -208,7 +226,7 @@ def main():
     torch.cuda.synchronize()
     assert int(status.max().item()) == 0, "synthetic clips must all be feasible"
 
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
@@ -225,7 +243,8 @@ def main():
         dist.barrier()
     clk = clocks.stop() if rank == 0 else None
     ms_total = t_start.elapsed_time(t_end)
-    emit_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    mel_ms = statistics.mean(m.elapsed_time(a) for m, a, b in ev)
+    emit_ms = statistics.mean(a.elapsed_time(b) for m, a, b in ev)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -250,6 +269,13 @@ def main():
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": round(emit_ms, 4)}
+    # secondary kernels, for the record (DESIGN.md "Measurement")
+    mel_flops = 3 * 2 * 2.0 * 200 * 208 * float(np.sum((mel_frames + 127) // 128 * 128))   # 3xTF32, Re+Im, padded tiles
+    mel_bytes = 4.0 * float(n_samp.astype(np.int64).sum()) + 2 * 4.0 * 80 * float(mel_frames.astype(np.int64).sum())
+    step_ms = ms_total / args.steps
+    kernels = {"k1_logmel_ms": round(mel_ms, 4), "k1_tf32_tflops": round(mel_flops / (mel_ms / 1e3) / 1e12, 1),
+               "k1_algorithmic_gbs": round(mel_bytes / (mel_ms / 1e3) / 1e9, 1),
+               "k2_emit_ms": round(emit_ms, 4), "k3_viterbi_and_rest_ms": round(step_ms - mel_ms - emit_ms, 4)}
 
     # ---- e2e + cpu baseline on rank 0's pinned pool ----------------------------------------
     e2e, cpu = None, None
@@ -269,10 +295,15 @@ def main():
             lab = lab_sets[i // pool_n][i % pool_n]
             return lab[:max(1, int(batch.t_len[i % pool_n]) // 3)]
 
+        wave_host = wave.cpu().pin_memory()
+        pool_wave = [wave_host[w_off[i]:w_off[i] + int(n_samp[i])] for i in range(pool_n)]
+
         def e2e_step():
             tot = 0
             for i in range(n_calls):
-                out = la.perform_viterbi_ctc(pool_pred[i % pool_n], [lab_for(i).tolist()])
+                j = i % pool_n
+                mel = LA.log_mel_spectrogram(pool_wave[j])                 # B1: host waveform -> device log-mel
+                out = la.perform_viterbi_ctc(pool_pred[j], [lab_for(i).tolist()])   # B2: host logits -> on/offsets
                 tot += len(out[0])
             return tot
         e2e_step()
@@ -288,14 +319,15 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_audio = float(sum(batch.durations[i % pool_n] for i in range(n_calls))) * world
-        h2d = float(sum(int(batch.t_len[i % pool_n]) for i in range(n_calls))) * V * 4
+        h2d = float(sum(int(batch.t_len[i % pool_n]) for i in range(n_calls))) * V * 4 + \
+            4.0 * float(sum(int(n_samp[i % pool_n]) for i in range(n_calls)))
         e2e = {"value": round(e2e_audio * args.e2e_steps / float(tt.item()), 1), "unit": "audio-s/s",
                "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": float(n_lab * 8 + n_calls * 12) * world,
                "steps": args.e2e_steps,
-               "call": "lyricalignment_b200.perform_viterbi_ctc(pinned_cpu_tensor[1,T,V], labels), one call per clip"}
+               "call": "per clip: audio.log_mel_spectrogram(pinned waveform) + perform_viterbi_ctc(pinned_cpu_tensor[1,T,V], labels)"}
         if rank == 0 and not args.skip_cpu:
             n_cpu = min(CPU_SAMPLE_CLIPS, pool_n)
-            v, kind, secs = time_cpu(pool_pred, batch.labels, batch.durations, n_cpu, 3)
+            v, kind, secs = time_cpu(pool_pred, batch.labels, batch.durations, n_cpu, 3, pool_wave)
             cpu = {"value": round(v, 1), "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": kind,
                    "sample": f"first {n_cpu} clips of the workload ({sum(batch.durations[:n_cpu]):.0f} audio-s), "
                              f"median of 3 passes, {secs:.2f} s per pass, host cpu_count={os.cpu_count()}"}
@@ -310,8 +342,8 @@ def main():
                                    f"V=21129 CTC decode, {plan.total_labels} syllables, {total_T} frames",
                        "l2_policy": f"inputs larger than L2 ({4.0 * total_T * V / 1e9:.1f} GB of logits resident in HBM per GPU)",
                        "parallelism": f"utterance-sharded x{world}" + (", NCCL gather of alignments in the step" if world > 1 else "")},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": plan.num_launches * args.steps, "clocks": clk,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": (plan.num_launches + 3) * args.steps, "clocks": clk,
         }
         print(json.dumps(line))
     plan.close()
@@ -328,12 +360,16 @@ def run_reference_arm(args, synth):
     pred = synth.planted_logits(sub, synth.V_HEAD, ctc=True, device="cpu", seed=114514)
     offs = np.concatenate([[0], np.cumsum(sub.t_len)])
     pool = [pred[offs[i]:offs[i + 1]].unsqueeze(0) for i in range(n)]
+    from oracle.logmel import log_mel_spectrogram_torch_f32
+    wave, w_off = synth.synthetic_waveforms(sub, device="cpu", seed=114514)
+    waves = [wave[w_off[i]:w_off[i] + int(sub.n_samples[i])] for i in range(n)]
     fn, kind = cpu_decode_fn()
     fn(pool[0][:, :8], [sub.labels[0][:1].tolist()])
 
     def step():
         for i in range(n):
-            fn(pool[i], [sub.labels[i].tolist()])
+            log_mel_spectrogram_torch_f32(waves[i])                   # whisper's CPU log-mel (align_model.py:84)
+            fn(pool[i], [sub.labels[i].tolist()])                     # utils/alignment.py decode
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()

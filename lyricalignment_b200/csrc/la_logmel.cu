@@ -265,8 +265,10 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                         float v;
                         if (n == kNfft / 2) v = odd ? 0.f : fwd;
                         else v = odd ? fwd - rev : fwd + rev;
-                        const float hi = __int_as_float(__float_as_int(v) & 0xffffe000);
-                        const float lo = v - hi;
+                        // round-to-nearest TF32 split; lo is pre-rounded too so the tensor core's
+                        // operand truncation is a no-op (|v - hi - lo| <= 2^-23 |v|)
+                        const float hi = __int_as_float((__float_as_int(v) + 0x1000) & 0xffffe000);
+                        const float lo = __int_as_float((__float_as_int(v - hi) + 0x1000) & 0xffffe000);
                         const int off = ki * kALbo + (r >> 3) * 128 + (r & 7) * 16 + kq * 4;
                         *reinterpret_cast<float*>(st + off) = hi;
                         *reinterpret_cast<float*>(st + kABytes + off) = lo;
@@ -358,7 +360,11 @@ static void tf32_split(double v, float* hi, float* lo) {
     float h;
     memcpy(&h, &u, 4);
     *hi = h;
-    *lo = (float)(v - (double)h);
+    float l = (float)(v - (double)h);
+    memcpy(&u, &l, 4);
+    u = (u + 0x1000u) & 0xffffe000u;          // pre-round lo as well: operand truncation becomes a no-op
+    memcpy(&l, &u, 4);
+    *lo = l;
 }
 
 // librosa.filters.mel(sr=16000, n_fft=400, n_mels=80): Slaney scale + Slaney area norm, fp32 out

@@ -80,3 +80,27 @@ def planted_logits(batch: ClipBatch, V: int = V_HEAD, ctc: bool = True, device="
     val_s = torch.from_numpy(np.concatenate(val_s).astype(np.float32)).to(device)
     z[rows_s, (V - 1) if ctc else 0] += val_s
     return z
+
+
+def synthetic_waveforms(batch: ClipBatch, device="cuda", seed: int = 114514):
+    """SURVEY.md 8(d) waveforms, concatenated (every clip start padded to a multiple of 4 samples so
+    the TMA path applies): 0.1 N(0,1) noise + 10 amplitude-modulated harmonics of 220 Hz, last 10 %
+    zeroed. Returns (wave [total] float32 on `device`, offsets int64 [B])."""
+    offs = np.zeros(len(batch.n_samples), np.int64)
+    pos = 0
+    for i, n in enumerate(batch.n_samples):
+        offs[i] = pos
+        pos += (int(n) + 3) // 4 * 4
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + 7)
+    wave = torch.empty(pos + 8, dtype=torch.float32, device=device)
+    wave.normal_(0.0, 0.1, generator=g)
+    for i, n in enumerate(batch.n_samples):
+        n = int(n)
+        t = torch.arange(n, device=device, dtype=torch.float32) / 16000.0
+        seg = wave[offs[i]:offs[i] + n]
+        env = 0.5 + 0.5 * torch.sin(2 * np.pi * 3.0 * t)
+        for h in range(1, 11):
+            seg += (0.3 / h) * torch.sin(2 * np.pi * 220.0 * h * t) * env
+        seg[int(0.9 * n):] = 0.0
+    return wave, offs
