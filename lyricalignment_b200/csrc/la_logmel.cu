@@ -19,13 +19,12 @@
 // One persistent CTA per SM, 128-frame tiles, warp-specialised:
 //   warp 0      producer: 1-D TMA bulk copies of the tile's waveform rows (130 hop rows of 640 B
 //               into a 656 B-pitch, bank-conflict-free staging area) and of the constant basis
-//               blocks (13 KB per half k-step, L2-resident) into a 6-deep ring;
+//               blocks (26 KB per k-step, L2-resident) into a 3-deep ring;
 //   warp 1      TMEM allocator + MMA issuer (one elected lane, 150 tcgen05.mma per tile);
-//   warps 4..7  transform: staged waveform -> folded, hi/lo-split A operand in the UMMA
-//               canonical no-swizzle K-major layout (bank-conflict-free both ways); then, per
-//               tile, the epilogue: TMEM -> registers, power, sparse mel projection (each FFT
-//               bin feeds <= 2 adjacent triangular filters), log10 clamp, coalesced stores and
-//               the running maximum.
+//   warps 8..15 transform: staged waveform -> folded, hi/lo-split A operands in the UMMA
+//               canonical no-swizzle K-major layout (bank-conflict-free both ways);
+//   warps 4..7  epilogue: TMEM -> registers, power, sparse mel projection (each FFT bin feeds
+//               <= 2 adjacent triangular filters), log10 clamp, coalesced stores, running max.
 // Clip-boundary tiles (reflect padding, ragged ends) are staged by the transform warps with
 // plain loads instead of TMA. A second tiny kernel applies the max-8 floor and (x+4)/4.
 #include <algorithm>
@@ -51,11 +50,13 @@ constexpr int kALbo = 2064;                 // bytes between K-adjacent core mat
 constexpr int kABytes = 2 * kALbo;          // one A operand (hi or lo) of one k-step
 constexpr int kBLbo = (kNpad / 8) * 128;    // 3328
 constexpr int kBBytes = 2 * kBLbo;          // 6656: one B operand (hi or lo) of one k-step
-constexpr int kStageBytes = 21632;          // 2*kABytes + 2*kBBytes = 21568, padded to 128
-constexpr int kStages = 6;
+constexpr int kStageBytes = 4 * kABytes + 4 * kBBytes;   // 43136: [Ae_hi Ae_lo Ao_hi Ao_lo | C_hi C_lo S_hi S_lo]
+constexpr int kStages = 3;
 constexpr int kRawBytes = kRawRows * kRawPitch * 4;   // 85280
-constexpr int kLogmelThreads = 256;
+constexpr int kXformWarps = 8;              // warps 8..15
+constexpr int kLogmelThreads = 512;
 constexpr uint32_t kTmemCols = 512;
+static_assert(kStageBytes % 128 == 0, "stage pitch");
 
 struct ClipDesc {
     int64_t wave_off;   // float offset of the clip's first sample
@@ -138,12 +139,18 @@ __device__ __forceinline__ float ordered_to_float(int k) {
     return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
 }
 
+__device__ __forceinline__ float rna_tf32(float x) {      // round-to-nearest TF32 (10 explicit mantissa bits)
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stages = smem;
     float* raw = reinterpret_cast<float*>(smem + kStages * kStageBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kRawBytes);
-    uint64_t* full = bars;                    // [kStages] B landed (tx) + 4 transform warps
+    uint64_t* full = bars;                    // [kStages] basis landed (tx) + 8 transform warps
     uint64_t* empty = bars + kStages;         // [kStages] MMAs of the stage retired
     uint64_t* raw_full = bars + 2 * kStages;
     uint64_t* raw_empty = raw_full + 1;
@@ -154,9 +161,9 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 5); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1 + kXformWarps); mbar_init(&empty[s], 1); }
         mbar_init(raw_full, 1);
-        mbar_init(raw_empty, 4);
+        mbar_init(raw_empty, kXformWarps);
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 4);
         mbar_fence_init();
@@ -185,12 +192,12 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 } else {
                     mbar_arrive(raw_full);             // the transform warps stage boundary tiles themselves
                 }
-                for (int hs = 0; hs < 2 * kKSteps; ++hs, ++it) {
+                for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                     const int s = it % kStages;
                     mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full[s], 2 * kBBytes);
-                    bulk_g2s(stages + s * kStageBytes + 2 * kABytes,
-                             reinterpret_cast<const unsigned char*>(p.basis) + (size_t)hs * 2 * kBBytes, 2 * kBBytes,
+                    mbar_arrive_expect_tx(&full[s], 4 * kBBytes);
+                    bulk_g2s(stages + s * kStageBytes + 4 * kABytes,
+                             reinterpret_cast<const unsigned char*>(p.basis) + (size_t)ks * 4 * kBBytes, 4 * kBBytes,
                              &full[s]);
                 }
             }
@@ -202,29 +209,33 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
                 mbar_wait(tmem_empty, (tl & 1) ^ 1);       // epilogue of the previous tile drained TMEM
                 tc_fence_after();
-                for (int hs = 0; hs < 2 * kKSteps; ++hs, ++it) {
+                for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                     const int s = it % kStages;
                     mbar_wait(&full[s], (it / kStages) & 1);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(stages + s * kStageBytes);
-                    const uint64_t a_hi = umma_desc(sa, kALbo, 128);
-                    const uint64_t a_lo = umma_desc(sa + kABytes, kALbo, 128);
-                    const uint64_t b_hi = umma_desc(sa + 2 * kABytes, kBLbo, 128);
-                    const uint64_t b_lo = umma_desc(sa + 2 * kABytes + kBBytes, kBLbo, 128);
-                    const uint32_t d = tmem_base + ((hs & 1) ? kNpad : 0);   // even -> Re, odd -> Im
-                    umma_tf32(d, a_hi, b_lo, kIdesc, hs >= 2 ? 1u : 0u);      // small terms first
-                    umma_tf32(d, a_lo, b_hi, kIdesc, 1u);
-                    umma_tf32(d, a_hi, b_hi, kIdesc, 1u);
+                    const uint32_t sb = sa + 4 * kABytes;
+                    const uint64_t ae_hi = umma_desc(sa, kALbo, 128), ae_lo = umma_desc(sa + kABytes, kALbo, 128);
+                    const uint64_t ao_hi = umma_desc(sa + 2 * kABytes, kALbo, 128), ao_lo = umma_desc(sa + 3 * kABytes, kALbo, 128);
+                    const uint64_t c_hi = umma_desc(sb, kBLbo, 128), c_lo = umma_desc(sb + kBBytes, kBLbo, 128);
+                    const uint64_t s_hi = umma_desc(sb + 2 * kBBytes, kBLbo, 128), s_lo = umma_desc(sb + 3 * kBBytes, kBLbo, 128);
+                    const uint32_t acc = ks > 0 ? 1u : 0u;
+                    umma_tf32(tmem_base, ae_hi, c_lo, kIdesc, acc);           // Re: small terms first
+                    umma_tf32(tmem_base, ae_lo, c_hi, kIdesc, 1u);
+                    umma_tf32(tmem_base, ae_hi, c_hi, kIdesc, 1u);
+                    umma_tf32(tmem_base + kNpad, ao_hi, s_lo, kIdesc, acc);   // Im
+                    umma_tf32(tmem_base + kNpad, ao_lo, s_hi, kIdesc, 1u);
+                    umma_tf32(tmem_base + kNpad, ao_hi, s_hi, kIdesc, 1u);
                     umma_commit(&empty[s]);
                 }
                 umma_commit(tmem_full);
             }
         }
-    } else if (warp >= 4) {
-        // ====================== transform + epilogue (128 threads) ==========================
-        const int wq = warp - 4;                   // TMEM lane quarter == warp % 4
-        const int row = wq * 32 + lane;            // frame row of this thread in the epilogue
-        const int et = tid - 128;
+    } else if (warp >= 8) {
+        // ====================== transform: staged waveform -> A operands (256 threads) =======
+        const int tw = warp - 8;
+        const int xt = tid - 256;
+        const int rsub = lane >> 2, kq = lane & 3;
         uint32_t it = 0, tl = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
             const ClipDesc c = p.clips[p.tile_clip[tile]];
@@ -236,42 +247,39 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 // reflect padding (torch.stft centre=True) and ragged clip ends, by plain loads
                 const float* x = p.wave + c.wave_off;
                 const int N = c.n_samples;
-                for (int idx = et; idx < kRawRows * kHop; idx += 128) {
+#pragma unroll 4
+                for (int idx = xt; idx < kRawRows * kHop; idx += 256) {
                     int64_t j = j0 + idx;
                     if (j < 0) j = -j;
                     if (j >= N) j = 2 * (int64_t)(N - 1) - j;
                     j = j < 0 ? 0 : (j >= N ? N - 1 : j);
                     raw[(idx / kHop) * kRawPitch + idx % kHop] = __ldg(x + j);
                 }
-                named_bar_sync(2, 128);
+                named_bar_sync(2, 256);
             }
-            // ---- A operand: fold + hi/lo split, 50 half k-steps -----------------------------
-            const int rsub = lane >> 2, kq = lane & 3;
-            for (int hs = 0; hs < 2 * kKSteps; ++hs, ++it) {
+            // sample s = r*160 + n of the tile sits at raw[r*164 + n + 4*(n/160)]
+            for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                 const int s = it % kStages;
                 mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
                 unsigned char* st = stages + s * kStageBytes;
-                const int kstep = hs >> 1;
-                const bool odd = hs & 1;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int r = wq * 32 + g * 8 + rsub;
+                for (int g = 0; g < 2; ++g) {
+                    const int r = tw * 16 + g * 8 + rsub;
+                    const float* rrow = raw + r * kRawPitch;
 #pragma unroll
                     for (int ki = 0; ki < 2; ++ki) {
-                        const int n = kstep * 8 + ki * 4 + kq + 1;           // 1..200
-                        const int sf = r * kHop + n, sr = r * kHop + kNfft - n;
-                        const float fwd = raw[(sf / kHop) * kRawPitch + sf % kHop];
-                        const float rev = raw[(sr / kHop) * kRawPitch + sr % kHop];
-                        float v;
-                        if (n == kNfft / 2) v = odd ? 0.f : fwd;
-                        else v = odd ? fwd - rev : fwd + rev;
-                        // round-to-nearest TF32 split; lo is pre-rounded too so the tensor core's
-                        // operand truncation is a no-op (|v - hi - lo| <= 2^-23 |v|)
-                        const float hi = __int_as_float((__float_as_int(v) + 0x1000) & 0xffffe000);
-                        const float lo = __int_as_float((__float_as_int(v - hi) + 0x1000) & 0xffffe000);
+                        const int n = ks * 8 + ki * 4 + kq + 1;              // 1..200
+                        const int m = kNfft - n;                             // 200..399
+                        const float fwd = rrow[n + (n >= kHop ? 4 : 0)];
+                        const float rev = rrow[m + 4 + (m >= 2 * kHop ? 4 : 0)];
+                        const float e = fwd + rev, o = fwd - rev;            // n = 200: e = 2 x[200] (basis row halved), o = 0
+                        const float e_hi = rna_tf32(e), o_hi = rna_tf32(o);
+                        const float e_lo = rna_tf32(e - e_hi), o_lo = rna_tf32(o - o_hi);
                         const int off = ki * kALbo + (r >> 3) * 128 + (r & 7) * 16 + kq * 4;
-                        *reinterpret_cast<float*>(st + off) = hi;
-                        *reinterpret_cast<float*>(st + kABytes + off) = lo;
+                        *reinterpret_cast<float*>(st + off) = e_hi;
+                        *reinterpret_cast<float*>(st + kABytes + off) = e_lo;
+                        *reinterpret_cast<float*>(st + 2 * kABytes + off) = o_hi;
+                        *reinterpret_cast<float*>(st + 3 * kABytes + off) = o_lo;
                     }
                 }
                 fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core
@@ -280,8 +288,15 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(raw_empty);      // staged waveform no longer needed
-
-            // ---- epilogue: power -> mel -> log10, straight out of TMEM ------------------------
+        }
+    } else if (warp >= 4) {
+        // ====================== epilogue: power -> mel -> log10, straight out of TMEM =========
+        const int wq = warp - 4;                   // TMEM lane quarter == warp % 4
+        const int row = wq * 32 + lane;
+        uint32_t tl = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
+            const ClipDesc c = p.clips[p.tile_clip[tile]];
+            const int f0 = (tile - c.tile0) * kTileM;
             mbar_wait(tmem_full, tl & 1);
             tc_fence_after();
             const int f = f0 + row;
@@ -303,6 +318,11 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 tmem_ld16(lane_base + cb, re);
                 tmem_ld16(lane_base + kNpad + cb, im);
                 tmem_ld_wait();
+                if (cb + 16 >= kNpad) {                 // all of TMEM is in registers: release it early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
+                }
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int k = cb + q;
@@ -317,9 +337,6 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 }
             }
             while (cur < kMels) { emit(cur, a0); a0 = a1; a1 = 0.f; ++cur; }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
 #pragma unroll
             for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if (lane == 0 && mx > -INFINITY) atomicMax(p.group_max + c.group, float_to_ordered(mx));
@@ -414,7 +431,8 @@ static cudaError_t ensure_tables(int device, const float** basis_out) {
                     double cv = 0.0, sv = 0.0;
                     if (b < kBins) {
                         const int ph = (int)(((long long)b * n) % kNfft);     // exact phase reduction
-                        cv = w * std::cos(2.0 * PI * ph / kNfft);
+                        // n = 200 folds onto itself: the kernel forms e[200] = 2 x[200], so halve its row
+                        cv = (n == kNfft / 2 ? 0.5 : 1.0) * w * std::cos(2.0 * PI * ph / kNfft);
                         sv = (n == kNfft / 2) ? 0.0 : -w * std::sin(2.0 * PI * ph / kNfft);
                     }
                     const size_t inner = (size_t)(kk >> 2) * (kBLbo / 4) + (size_t)(b >> 3) * 32 + (b & 7) * 4 + (kk & 3);
