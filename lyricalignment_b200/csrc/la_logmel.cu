@@ -21,12 +21,13 @@
 //               into a 656 B-pitch, bank-conflict-free staging area) and of the constant basis
 //               blocks (26 KB per k-step, L2-resident) into a 3-deep ring;
 //   warp 1      TMEM allocator + MMA issuer (one elected lane, 150 tcgen05.mma per tile);
-//   warps 8..15 transform: staged waveform -> folded, hi/lo-split A operands in the UMMA
+//   warps 12..19 transform: staged waveform -> folded, hi/lo-split A operands in the UMMA
 //               canonical no-swizzle K-major layout (bank-conflict-free both ways);
-//   warps 4..7  epilogue: TMEM -> registers, power, sparse mel projection (each FFT bin feeds
-//               <= 2 adjacent triangular filters), log10 clamp, coalesced stores, running max.
+//   warps 4..11 epilogue (two warps per TMEM lane quarter, bins split in two): TMEM ->
+//               registers, power, sparse mel projection (each FFT bin feeds <= 2 adjacent
+//               triangular filters), coalesced stores of the mel power, running max.
 // Clip-boundary tiles (reflect padding, ragged ends) are staged by the transform warps with
-// plain loads instead of TMA. A second tiny kernel applies the max-8 floor and (x+4)/4.
+// plain loads instead of TMA. A second small kernel applies log10, the max-8 floor and (x+4)/4.
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -53,8 +54,10 @@ constexpr int kBBytes = 2 * kBLbo;          // 6656: one B operand (hi or lo) of
 constexpr int kStageBytes = 4 * kABytes + 4 * kBBytes;   // 43136: [Ae_hi Ae_lo Ao_hi Ao_lo | C_hi C_lo S_hi S_lo]
 constexpr int kStages = 3;
 constexpr int kRawBytes = kRawRows * kRawPitch * 4;   // 85280
-constexpr int kXformWarps = 8;              // warps 8..15
-constexpr int kLogmelThreads = 512;
+constexpr int kXformWarps = 8;              // warps 12..19
+constexpr int kEpiWarps = 8;                // warps 4..11: two per TMEM lane quarter, bins split at kSplit
+constexpr int kSplit = 96;                  // bins [0, 96) -> warps 4..7, [96, 201) -> warps 8..11
+constexpr int kLogmelThreads = 640;
 constexpr uint32_t kTmemCols = 512;
 static_assert(kStageBytes % 128 == 0, "stage pitch");
 
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
     uint64_t* tmem_full = raw_full + 2;
     uint64_t* tmem_empty = raw_full + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_full + 4);
+    float* xfer = reinterpret_cast<float*>(raw_full + 6);   // [2 tiles][2 filters][128 rows] partial sums at the bin split
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
         mbar_init(raw_full, 1);
         mbar_init(raw_empty, kXformWarps);
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, kEpiWarps);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -231,10 +235,10 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 umma_commit(tmem_full);
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 12) {
         // ====================== transform: staged waveform -> A operands (256 threads) =======
-        const int tw = warp - 8;
-        const int xt = tid - 256;
+        const int tw = warp - 12;
+        const int xt = tid - 384;
         const int rsub = lane >> 2, kq = lane & 3;
         uint32_t it = 0, tl = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
@@ -290,9 +294,16 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             if (lane == 0) mbar_arrive(raw_empty);      // staged waveform no longer needed
         }
     } else if (warp >= 4) {
-        // ====================== epilogue: power -> mel -> log10, straight out of TMEM =========
-        const int wq = warp - 4;                   // TMEM lane quarter == warp % 4
+        // ====================== epilogue: power -> mel, straight out of TMEM (256 threads) ====
+        // Two warps share each TMEM lane quarter and split the 201 bins at kSplit. Exactly two
+        // filters (ms, ms + 1, ms = first filter fed by bin kSplit) receive power from both sides:
+        // the low half hands its partial sums over through shared memory. The mel POWER is stored;
+        // log10 / floor / scaling happen in logmel_finalize_kernel (max is monotone under log10).
+        const int half = warp >= 8 ? 1 : 0;
+        const int wq = warp & 3;                   // TMEM lane quarter == warp % 4
         const int row = wq * 32 + lane;
+        const int ms = c_mel_lo[kSplit];
+        const int cb0 = half ? kSplit : 0, cb1 = half ? kNpad : kSplit;
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
             const ClipDesc c = p.clips[p.tile_clip[tile]];
@@ -302,23 +313,24 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             const int f = f0 + row;
             const bool valid = f < c.n_frames;
             float* outp = p.out + c.out_off + f;
-            float mx = -INFINITY;
-            int cur = 0;
-            float a0 = 0.f, a1 = 0.f;
+            float mx = 0.f;
+            int cur = half ? ms : 0;
+            float a0 = 0.f, a1 = 0.f, p0 = 0.f, p1 = 0.f;
             auto emit = [&](int m, float v) {
-                const float lg = log10f(fmaxf(v, 1e-10f));
-                if (valid && m < kMels) {
-                    outp[(int64_t)m * c.out_stride] = lg;
-                    mx = fmaxf(mx, lg);
+                if (half && m <= ms + 1) {             // straddling filters: keep until the low half reports
+                    if (m == ms) p0 = v; else p1 = v;
+                } else if (valid && m < kMels) {
+                    outp[(int64_t)m * c.out_stride] = v;
+                    mx = fmaxf(mx, v);
                 }
             };
             const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
-            for (int cb = 0; cb < kNpad; cb += 16) {
+            for (int cb = cb0; cb < cb1; cb += 16) {
                 uint32_t re[16], im[16];
                 tmem_ld16(lane_base + cb, re);
                 tmem_ld16(lane_base + kNpad + cb, im);
                 tmem_ld_wait();
-                if (cb + 16 >= kNpad) {                 // all of TMEM is in registers: release it early
+                if (cb + 16 >= cb1) {                   // this warp's share of TMEM is in registers
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tmem_empty);
@@ -336,10 +348,25 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                     }
                 }
             }
-            while (cur < kMels) { emit(cur, a0); a0 = a1; a1 = 0.f; ++cur; }
+            float* xf = xfer + (tl & 1) * 256;
+            if (!half) {
+                while (cur < ms) { emit(cur, a0); a0 = a1; a1 = 0.f; ++cur; }
+                xf[row] = a0;                           // partial of filter ms
+                xf[128 + row] = a1;                     // partial of filter ms + 1
+                named_bar_sync(3, 256);
+            } else {
+                while (cur < kMels) { emit(cur, a0); a0 = a1; a1 = 0.f; ++cur; }
+                named_bar_sync(3, 256);
+                if (valid) {
+                    const float v0 = p0 + xf[row], v1 = p1 + xf[128 + row];
+                    outp[(int64_t)ms * c.out_stride] = v0;
+                    outp[(int64_t)(ms + 1) * c.out_stride] = v1;
+                    mx = fmaxf(mx, fmaxf(v0, v1));
+                }
+            }
 #pragma unroll
             for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0 && mx > -INFINITY) atomicMax(p.group_max + c.group, float_to_ordered(mx));
+            if (lane == 0) atomicMax(p.group_max + c.group, __float_as_int(mx));   // mx >= 0: int order == float order
         }
     }
 
@@ -351,15 +378,17 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
     }
 }
 
-// out = (max(x, gmax - 8) + 4) / 4 over the valid frames of every clip
+// mel power -> log10(clamp 1e-10) -> max(x, gmax - 8) -> (x + 4) / 4 over the valid frames of every clip
 __global__ void logmel_finalize_kernel(const LogmelParams p) {
     const ClipDesc c = p.clips[blockIdx.y];
-    const float floor_v = ordered_to_float(p.group_max[c.group]) - 8.0f;
+    const float gmax = log10f(fmaxf(__int_as_float(p.group_max[c.group]), 1e-10f));
+    const float floor_v = gmax - 8.0f;
     const int total = kMels * c.n_frames;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int m = i / c.n_frames, f = i - m * c.n_frames;
         float* q = p.out + c.out_off + (int64_t)m * c.out_stride + f;
-        *q = (fmaxf(*q, floor_v) + 4.0f) / 4.0f;
+        const float x = log10f(fmaxf(*q, 1e-10f));
+        *q = (fmaxf(x, floor_v) + 4.0f) / 4.0f;
     }
 }
 
@@ -476,7 +505,7 @@ static cudaError_t ensure_tables(int device, const float** basis_out) {
     return cudaSuccess;
 }
 
-size_t logmel_smem_bytes() { return (size_t)kStages * kStageBytes + kRawBytes + 256; }
+size_t logmel_smem_bytes() { return (size_t)kStages * kStageBytes + kRawBytes + 128 + 2 * 2 * 128 * 4; }
 
 }  // namespace la
 
@@ -525,7 +554,7 @@ static int logmel_run(const float* d_wave, float* d_out, const std::vector<la::C
     p.n_tiles = n_tiles; p.n_clips = (int)clips.size();
     p.basis = basis;
     p.group_max = reinterpret_cast<int*>(ws + o_max);
-    fill_int_kernel<<<(n_groups + 255) / 256, 256, 0, stream>>>(p.group_max, n_groups, INT32_MIN);
+    fill_int_kernel<<<(n_groups + 255) / 256, 256, 0, stream>>>(p.group_max, n_groups, 0);   // 0.0f: powers are >= 0
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const size_t smem = logmel_smem_bytes();
