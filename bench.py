@@ -262,7 +262,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "k2_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("dram_bytes_per_frame") * total_T   # ncu, per frame, scaled to this launch
         except Exception:
             traffic = None
     roofline = {"kernel": "la::emit_kernel<CTC> (K2 fused log-softmax + gather)", "bound": "hbm",

@@ -32,6 +32,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -80,7 +81,8 @@ struct LogmelParams {
     int n_tiles;
     int n_clips;
     const float* basis;           // [25][even: C_hi, C_lo | odd: S_hi, S_lo] canonical UMMA layout
-    int* group_max;               // ordered-int encoded running maxima
+    int* group_max;               // running maxima of the mel power (bit pattern of a float >= 0)
+    int dbg;                      // LA_LOGMEL_DBG bisect knobs (perf triage only): 1 skip epilogue math, 2 skip transform math, 4 skip basis loads
 };
 
 __constant__ float c_mel_w0[kBins];
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                     const int s = it % kStages;
                     mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    if (p.dbg & 4) { mbar_arrive(&full[s]); continue; }
                     mbar_arrive_expect_tx(&full[s], 4 * kBBytes);
                     bulk_g2s(stages + s * kStageBytes + 4 * kABytes,
                              reinterpret_cast<const unsigned char*>(p.basis) + (size_t)ks * 4 * kBBytes, 4 * kBBytes,
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 const int s = it % kStages;
                 mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
                 unsigned char* st = stages + s * kStageBytes;
+                if (!(p.dbg & 2))
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     const int r = tw * 16 + g * 8 + rsub;
@@ -325,6 +329,12 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 }
             };
             const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+            if (p.dbg & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty);
+                continue;
+            }
             for (int cb = cb0; cb < cb1; cb += 16) {
                 uint32_t re[16], im[16];
                 tmem_ld16(lane_base + cb, re);
@@ -554,6 +564,7 @@ static int logmel_run(const float* d_wave, float* d_out, const std::vector<la::C
     p.n_tiles = n_tiles; p.n_clips = (int)clips.size();
     p.basis = basis;
     p.group_max = reinterpret_cast<int*>(ws + o_max);
+    { const char* d = getenv("LA_LOGMEL_DBG"); p.dbg = d ? atoi(d) : 0; }
     fill_int_kernel<<<(n_groups + 255) / 256, 256, 0, stream>>>(p.group_max, n_groups, 0);   // 0.0f: powers are >= 0
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
