@@ -25,7 +25,7 @@ from . import _lib
 from ._lib import MODE_CE, MODE_CTC, MODE_LOGP
 
 __all__ = ["perform_viterbi_ctc", "perform_viterbi", "run_viterbi_core", "get_mae", "align",
-           "AlignResult", "AlignPlan"]
+           "align_clips", "AlignResult", "AlignPlan"]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -201,6 +201,43 @@ def align(prediction, labels, mode: int = MODE_CTC, device: int | None = None) -
         return _run_host(plan, prediction.contiguous().view(B * T, V))
     finally:
         plan.close()
+
+
+def align_clips(logits2d: torch.Tensor, t_len, labels, mode: int = MODE_CTC, device: int | None = None,
+                staging_bytes: int = 0) -> AlignResult:
+    """Ragged batch in one call: ``logits2d`` is float32 [sum(t_len), V] with clip u owning rows
+    [sum(t_len[:u]), +t_len[u]); ``labels`` one row of class ids per clip. CUDA tensor -> K2 + K3 in
+    place; CPU tensor (pin it) -> streamed through the double-buffered host path, so the H2D copy
+    of clip u+1 overlaps the kernels of clip u. This is the call to use for a whole dataset; the
+    reference-shaped ``perform_viterbi*`` wrappers go through the same code with B padded clips."""
+    _require_cuda()
+    if logits2d.dim() != 2 or logits2d.dtype != torch.float32:
+        raise ValueError("logits2d must be float32 [frames, vocab]")
+    V = logits2d.shape[1]
+    rows = _label_rows(labels)
+    t_len = np.ascontiguousarray(t_len, dtype=np.int32)
+    if len(rows) != len(t_len) or int(t_len.sum()) != logits2d.shape[0]:
+        raise ValueError("t_len / labels do not match the logits")
+    l_len, cols = _resolve_columns(rows, V - 2 if mode == MODE_CTC else V - 1)
+    if logits2d.is_cuda:
+        dev = logits2d.device.index
+        with torch.cuda.device(dev):
+            plan = AlignPlan(mode, V, t_len, l_len, cols, dev)
+            try:
+                return _run_device(plan, logits2d if logits2d.stride(1) == 1 else logits2d.contiguous())
+            finally:
+                plan.close()
+    dev = torch.cuda.current_device() if device is None else device
+    plan = AlignPlan(mode, V, t_len, l_len, cols, dev)
+    try:
+        return _run_host(plan, logits2d.contiguous(), staging_bytes)
+    finally:
+        plan.close()
+
+
+def onoff_seconds(res: AlignResult, hop_size_second: float = 0.02):
+    """AlignResult -> the reference's nested [[onset, offset], ...] lists (raises like it does)."""
+    return _to_onoff(res, hop_size_second)
 
 
 def _to_onoff(res: AlignResult, hop_size_second: float) -> List[List[List[float]]]:

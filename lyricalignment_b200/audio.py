@@ -85,11 +85,13 @@ def log_mel_spectrogram(audio, n_mels: int = N_MELS, padding: int = 0, device=No
 def log_mel_spectrogram_ragged(wave: torch.Tensor, offsets: Sequence[int], n_samples: Sequence[int],
                                out: torch.Tensor | None = None, out_offsets=None, out_strides=None):
     """Many independent clips (each one its own whisper call, i.e. its own maximum) in ONE launch.
-    wave: CUDA float32 [total]; clip c = wave[offsets[c] : offsets[c] + n_samples[c]].
+    wave: float32 [total], CUDA or (pinned) host; clip c = wave[offsets[c] : offsets[c] + n_samples[c]].
     Returns (out, out_offsets, frames): out is a flat CUDA buffer, clip c's [80, frames[c]] matrix
     starts at out_offsets[c] with row stride out_strides[c] (= frames[c] by default)."""
     lib = _lib.load()
-    assert wave.is_cuda and wave.dtype == torch.float32 and wave.is_contiguous()
+    assert wave.dtype == torch.float32 and wave.is_contiguous()
+    if not wave.is_cuda:      # host waveforms (pin them): one async H2D, then the launch
+        wave = wave.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
     dev = wave.device
     off = np.ascontiguousarray(offsets, dtype=np.int64)
     ns = np.ascontiguousarray(n_samples, dtype=np.int32)
