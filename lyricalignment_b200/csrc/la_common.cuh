@@ -50,7 +50,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// sub-block barrier over `nthreads` threads (whole warps). bar.sync is the .aligned form: every
+// lane of a participating warp must execute it together, so reconverge first.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    __syncwarp();
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 

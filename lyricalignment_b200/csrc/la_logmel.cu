@@ -363,16 +363,15 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 while (cur < ms) { emit(cur, a0); a0 = a1; a1 = 0.f; ++cur; }
                 xf[row] = a0;                           // partial of filter ms
                 xf[128 + row] = a1;                     // partial of filter ms + 1
-                named_bar_sync(3, 256);
             } else {
                 while (cur < kMels) { emit(cur, a0); a0 = a1; a1 = 0.f; ++cur; }
-                named_bar_sync(3, 256);
-                if (valid) {
-                    const float v0 = p0 + xf[row], v1 = p1 + xf[128 + row];
-                    outp[(int64_t)ms * c.out_stride] = v0;
-                    outp[(int64_t)(ms + 1) * c.out_stride] = v1;
-                    mx = fmaxf(mx, fmaxf(v0, v1));
-                }
+            }
+            named_bar_sync(3, 256);                     // both halves, one barrier instruction
+            if (half && valid) {
+                const float v0 = p0 + xf[row], v1 = p1 + xf[128 + row];
+                outp[(int64_t)ms * c.out_stride] = v0;
+                outp[(int64_t)(ms + 1) * c.out_stride] = v1;
+                mx = fmaxf(mx, fmaxf(v0, v1));
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));

@@ -35,8 +35,9 @@ __device__ __forceinline__ double shfl_up_f64(double v, int delta) {
     return __hiloint2double(hi, lo);
 }
 
-// K = pairs per thread, WIDE = all warps of the CTA work on one utterance
-template <int K, bool WIDE>
+// K = pairs per thread, WIDE = all warps of the CTA work on one utterance, DUMP = parity
+// instrumentation (full fp64 table to global memory; compiled out of the production kernels)
+template <int K, bool WIDE, bool DUMP>
 __global__ void __launch_bounds__(WIDE ? 1024 : 128) viterbi_kernel(const VitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 128) viterbi_kernel(const VitPar
                     if (lane == 31) xchg[warp] = pl[K - 1];
                     __syncthreads();
                 }
-                if (p.dp_dump) {
+                if (DUMP) {
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         if (pair0 + j <= L) p.dp_dump[2 * (pair0 + j)] = pb[j];
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 128) viterbi_kernel(const VitPar
                 if (lane == 31) xchg[(t & 1) * nwarps + warp] = pl[K - 1];
                 __syncthreads();
             }
-            if (p.dp_dump) {
+            if (DUMP) {
                 double* drow = p.dp_dump + (int64_t)t * (2 * L + 1);
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
@@ -252,9 +253,16 @@ size_t viterbi_smem_bytes(int row_floats_max, int chunk, int groups, int nwarps,
 
 template <int K, bool WIDE>
 static cudaError_t launch_one(const VitParams& p, int threads, int grid, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(viterbi_kernel<K, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    viterbi_kernel<K, WIDE><<<grid, threads, smem, stream>>>(p);
+    cudaError_t e;
+    if (p.dp_dump) {
+        e = cudaFuncSetAttribute(viterbi_kernel<K, WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        viterbi_kernel<K, WIDE, true><<<grid, threads, smem, stream>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(viterbi_kernel<K, WIDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        viterbi_kernel<K, WIDE, false><<<grid, threads, smem, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
