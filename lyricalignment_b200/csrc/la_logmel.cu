@@ -85,9 +85,19 @@ struct LogmelParams {
     int dbg;                      // LA_LOGMEL_DBG bisect knobs (perf triage only): 1 skip epilogue math, 2 skip transform math, 4 skip basis loads
 };
 
-__constant__ float c_mel_w0[kBins];
-__constant__ float c_mel_w1[kBins];
-__constant__ int c_mel_lo[kBins];
+// LA_LOGMEL_DBG & 8: CTA 0 timestamps its first 8 tiles (perf triage only)
+__device__ unsigned long long g_trace[4 * 8 * 32];
+__device__ __forceinline__ void trace(int dbg, int role, uint32_t tl, int ev) {
+    if ((dbg & 8) && blockIdx.x == 0 && tl < 8) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[(role * 8 + tl) * 32 + ev] = t;
+    }
+}
+
+// per FFT bin k: {w0, w1, bits(nf), bits(m_lo)}: weights into filters m_lo[k], m_lo[k]+1, and how many
+// filters complete (nf = m_lo[k] - m_lo[k-1] in {0,1,2}) before bin k is accumulated
+__constant__ float4 c_mel[kBins];
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -162,7 +172,6 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
     uint64_t* tmem_full = raw_full + 2;
     uint64_t* tmem_empty = raw_full + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_full + 4);
-    float* xfer = reinterpret_cast<float*>(raw_full + 6);   // [2 tiles][2 filters][128 rows] partial sums at the bin split
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -190,6 +199,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
                 const bool interior = j0 >= 0 && j0 + kRawRows * kHop <= c.n_samples && (c.wave_off & 3) == 0;
                 mbar_wait(raw_empty, (tl & 1) ^ 1);
+                trace(p.dbg, 3, tl, 0);
                 if (interior) {
                     mbar_arrive_expect_tx(raw_full, kRawRows * kHop * 4);
                     const float* src = p.wave + c.wave_off + j0;
@@ -198,9 +208,11 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 } else {
                     mbar_arrive(raw_full);             // the transform warps stage boundary tiles themselves
                 }
+                trace(p.dbg, 3, tl, 1);
                 for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                     const int s = it % kStages;
                     mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    trace(p.dbg, 3, tl, 2 + ks);
                     if (p.dbg & 4) { mbar_arrive(&full[s]); continue; }
                     mbar_arrive_expect_tx(&full[s], 4 * kBBytes);
                     bulk_g2s(stages + s * kStageBytes + 4 * kABytes,
@@ -216,10 +228,12 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
                 mbar_wait(tmem_empty, (tl & 1) ^ 1);       // epilogue of the previous tile drained TMEM
                 tc_fence_after();
+                trace(p.dbg, 0, tl, 0);
                 for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                     const int s = it % kStages;
                     mbar_wait(&full[s], (it / kStages) & 1);
                     tc_fence_after();
+                    trace(p.dbg, 0, tl, 1 + ks);
                     const uint32_t sa = smem_u32(stages + s * kStageBytes);
                     const uint32_t sb = sa + 4 * kABytes;
                     const uint64_t ae_hi = umma_desc(sa, kALbo, 128), ae_lo = umma_desc(sa + kABytes, kALbo, 128);
@@ -236,6 +250,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                     umma_commit(&empty[s]);
                 }
                 umma_commit(tmem_full);
+                trace(p.dbg, 0, tl, 26);
             }
         }
     } else if (warp >= 12) {
@@ -250,6 +265,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
             const bool interior = j0 >= 0 && j0 + kRawRows * kHop <= c.n_samples && (c.wave_off & 3) == 0;
             mbar_wait(raw_full, tl & 1);
+            if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 0);
             if (!interior) {
                 // reflect padding (torch.stft centre=True) and ragged clip ends, by plain loads
                 const float* x = p.wave + c.wave_off;
@@ -268,6 +284,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                 const int s = it % kStages;
                 mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 1 + ks);
                 unsigned char* st = stages + s * kStageBytes;
                 if (!(p.dbg & 2))
 #pragma unroll
@@ -296,37 +313,41 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(raw_empty);      // staged waveform no longer needed
+            if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 26);
         }
     } else if (warp >= 4) {
         // ====================== epilogue: power -> mel, straight out of TMEM (256 threads) ====
         // Two warps share each TMEM lane quarter and split the 201 bins at kSplit. Exactly two
-        // filters (ms, ms + 1, ms = first filter fed by bin kSplit) receive power from both sides:
-        // the low half hands its partial sums over through shared memory. The mel POWER is stored;
-        // log10 / floor / scaling happen in logmel_finalize_kernel (max is monotone under log10).
+        // filters (ms, ms + 1, ms = first filter fed by bin kSplit) receive power from both sides.
+        // The mel POWER is stored; log10 / floor / scaling happen in logmel_finalize_kernel (max is
+        // monotone under log10). The loop body is kept small on purpose: the first version unrolled
+        // to 3200 instructions and spent its time in instruction fetch.
         const int half = warp >= 8 ? 1 : 0;
         const int wq = warp & 3;                   // TMEM lane quarter == warp % 4
         const int row = wq * 32 + lane;
-        const int ms = c_mel_lo[kSplit];
+        const int ms = __float_as_int(c_mel[kSplit].w);
         const int cb0 = half ? kSplit : 0, cb1 = half ? kNpad : kSplit;
+        const int cur0 = half ? ms : 0;
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
             const ClipDesc c = p.clips[p.tile_clip[tile]];
             const int f0 = (tile - c.tile0) * kTileM;
             mbar_wait(tmem_full, tl & 1);
             tc_fence_after();
+            if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 0);
             const int f = f0 + row;
             const bool valid = f < c.n_frames;
+            const int64_t ostride = c.out_stride;
             float* outp = p.out + c.out_off + f;
+            float* optr = outp + cur0 * ostride;    // where the filter held in a0 will be stored
             float mx = 0.f;
-            int cur = half ? ms : 0;
-            float a0 = 0.f, a1 = 0.f, p0 = 0.f, p1 = 0.f;
-            auto emit = [&](int m, float v) {
-                if (half && m <= ms + 1) {             // straddling filters: keep until the low half reports
-                    if (m == ms) p0 = v; else p1 = v;
-                } else if (valid && m < kMels) {
-                    outp[(int64_t)m * c.out_stride] = v;
-                    mx = fmaxf(mx, v);
-                }
+            int cur = cur0;
+            float a0 = 0.f, a1 = 0.f;
+            auto flush = [&]() {                    // filter `cur` is complete: store its power
+                if (valid) *optr = a0;
+                mx = fmaxf(mx, a0);
+                optr += ostride;
+                a0 = a1; a1 = 0.f; ++cur;
             };
             const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
             if (p.dbg & 1) {
@@ -335,6 +356,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 if (lane == 0) mbar_arrive(tmem_empty);
                 continue;
             }
+#pragma unroll 1
             for (int cb = cb0; cb < cb1; cb += 16) {
                 uint32_t re[16], im[16];
                 tmem_ld16(lane_base + cb, re);
@@ -348,34 +370,39 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int k = cb + q;
-                    if (k < kBins) {
+                    if (k < kBins) {                    // false only for the 7 padding columns
+                        const float4 mw = c_mel[k];     // warp-uniform constant load
                         const float xr = __uint_as_float(re[q]), xi = __uint_as_float(im[q]);
                         const float pw = xr * xr + xi * xi;
-                        const int ml = c_mel_lo[k];
-                        while (cur < ml) { emit(cur, a0); a0 = a1; a1 = 0.f; ++cur; }
-                        a0 = fmaf(c_mel_w0[k], pw, a0);
-                        a1 = fmaf(c_mel_w1[k], pw, a1);
+                        const int nf = (q == 0 && cb == cb0) ? 0 : __float_as_int(mw.z);
+                        if (nf > 0) {
+                            flush();
+                            if (nf > 1) flush();
+                        }
+                        a0 = fmaf(mw.x, pw, a0);
+                        a1 = fmaf(mw.y, pw, a1);
                     }
                 }
             }
-            float* xf = xfer + (tl & 1) * 256;
+            // Filters ms and ms + 1 are fed from both halves: the high half stores its partial
+            // sums like any other filter, the low half adds its own after the barrier.
             if (!half) {
-                while (cur < ms) { emit(cur, a0); a0 = a1; a1 = 0.f; ++cur; }
-                xf[row] = a0;                           // partial of filter ms
-                xf[128 + row] = a1;                     // partial of filter ms + 1
+                while (cur < ms) flush();
             } else {
-                while (cur < kMels) { emit(cur, a0); a0 = a1; a1 = 0.f; ++cur; }
+                while (cur < kMels) flush();
             }
             named_bar_sync(3, 256);                     // both halves, one barrier instruction
-            if (half && valid) {
-                const float v0 = p0 + xf[row], v1 = p1 + xf[128 + row];
-                outp[(int64_t)ms * c.out_stride] = v0;
-                outp[(int64_t)(ms + 1) * c.out_stride] = v1;
+            if (!half && valid) {
+                float* o0 = outp + ms * ostride;
+                const float v0 = *o0 + a0, v1 = o0[ostride] + a1;
+                *o0 = v0;
+                o0[ostride] = v1;
                 mx = fmaxf(mx, fmaxf(v0, v1));
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if (lane == 0) atomicMax(p.group_max + c.group, __float_as_int(mx));   // mx >= 0: int order == float order
+            if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 1);
         }
     }
 
@@ -489,24 +516,28 @@ static cudaError_t ensure_tables(int device, const float** basis_out) {
     if (!g_tab.const_done[device]) {
         std::vector<float> W;
         build_mel(W);
-        float w0[kBins], w1[kBins];
-        int lo[kBins];
+        float4 tab[kBins];
         int prev = 0;
         for (int k = 0; k < kBins; ++k) {
             int first = -1;
             for (int m = 0; m < kMels; ++m)
                 if (W[(size_t)m * kBins + k] != 0.f) { first = m; break; }
-            if (first < 0) { lo[k] = prev; w0[k] = 0.f; w1[k] = 0.f; continue; }
-            lo[k] = first;
-            w0[k] = W[(size_t)first * kBins + k];
-            w1[k] = first + 1 < kMels ? W[(size_t)(first + 1) * kBins + k] : 0.f;
-            prev = first;
+            float w0 = 0.f, w1 = 0.f;
+            int lo = prev;
+            if (first >= 0) {
+                lo = first;
+                w0 = W[(size_t)first * kBins + k];
+                w1 = first + 1 < kMels ? W[(size_t)(first + 1) * kBins + k] : 0.f;
+            }
+            const int nf = k == 0 ? 0 : lo - prev;
+            if (nf < 0 || nf > 2) return cudaErrorInvalidValue;     // the epilogue flushes at most twice per bin
+            float fnf, flo;
+            memcpy(&fnf, &nf, 4);
+            memcpy(&flo, &lo, 4);
+            tab[k] = make_float4(w0, w1, fnf, flo);
+            prev = lo;
         }
-        cudaError_t e = cudaMemcpyToSymbol(c_mel_w0, w0, sizeof(w0));
-        if (e != cudaSuccess) return e;
-        e = cudaMemcpyToSymbol(c_mel_w1, w1, sizeof(w1));
-        if (e != cudaSuccess) return e;
-        e = cudaMemcpyToSymbol(c_mel_lo, lo, sizeof(lo));
+        cudaError_t e = cudaMemcpyToSymbol(c_mel, tab, sizeof(tab));
         if (e != cudaSuccess) return e;
         g_tab.const_done[device] = true;
     }
@@ -514,7 +545,7 @@ static cudaError_t ensure_tables(int device, const float** basis_out) {
     return cudaSuccess;
 }
 
-size_t logmel_smem_bytes() { return (size_t)kStages * kStageBytes + kRawBytes + 128 + 2 * 2 * 128 * 4; }
+size_t logmel_smem_bytes() { return (size_t)kStages * kStageBytes + kRawBytes + 128; }
 
 }  // namespace la
 
@@ -579,6 +610,11 @@ static int logmel_run(const float* d_wave, float* d_out, const std::vector<la::C
 }
 
 extern "C" {
+
+// perf triage only (not part of the public header): copies the LA_LOGMEL_DBG&8 timestamps out
+int la_debug_logmel_trace(unsigned long long* h_out) {
+    return cudaMemcpyFromSymbol(h_out, la::g_trace, sizeof(unsigned long long) * 4 * 8 * 32) == cudaSuccess ? 0 : -2;
+}
 
 size_t la_logmel_workspace_bytes(int n_clips, int64_t total_samples) {
     if (n_clips < 0 || total_samples < 0) return 0;
