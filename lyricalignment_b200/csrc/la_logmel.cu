@@ -344,8 +344,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             int cur = cur0;
             float a0 = 0.f, a1 = 0.f;
             auto flush = [&]() {                    // filter `cur` is complete: store its power
-                if (valid) *optr = a0;
-                mx = fmaxf(mx, a0);
+                if (valid) { *optr = a0; mx = fmaxf(mx, a0); }   // rows past the clip's last frame hold garbage
                 optr += ostride;
                 a0 = a1; a1 = 0.f; ++cur;
             };
