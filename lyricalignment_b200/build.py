@@ -22,7 +22,7 @@ NVCC_FLAGS = [
 
 
 def _newest_source_mtime() -> float:
-    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.startswith("__")]
     paths.append(os.path.join(os.path.dirname(HERE), "include", "lyricalign.h"))
     return max(os.path.getmtime(p) for p in paths)
 
@@ -31,6 +31,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= _newest_source_mtime():
         return SO_PATH
     os.makedirs(OUT_DIR, exist_ok=True)
+    if not os.path.exists(os.path.join(CSRC, "la_mel_table.inc")):      # committed; regenerate if missing
+        subprocess.check_call([sys.executable, os.path.join(CSRC, "gen_mel_table.py")])
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", SO_PATH,
            *[os.path.join(CSRC, s) for s in SOURCES], "-lcuda"]

@@ -39,6 +39,7 @@
 
 #include "../../include/lyricalign.h"
 #include "la_common.cuh"
+#include "la_mel_table.inc"
 
 namespace la {
 
@@ -57,7 +58,7 @@ constexpr int kStages = 3;
 constexpr int kRawBytes = kRawRows * kRawPitch * 4;   // 85280
 constexpr int kXformWarps = 8;              // warps 12..19
 constexpr int kEpiWarps = 8;                // warps 4..11: two per TMEM lane quarter, bins split at kSplit
-constexpr int kSplit = 96;                  // bins [0, 96) -> warps 4..7, [96, 201) -> warps 8..11
+constexpr int kSplit = LA_MEL_SPLIT;        // bins [0, 96) -> warps 4..7, [96, 201) -> warps 8..11
 constexpr int kLogmelThreads = 640;
 constexpr uint32_t kTmemCols = 512;
 static_assert(kStageBytes % 128 == 0, "stage pitch");
@@ -95,9 +96,7 @@ __device__ __forceinline__ void trace(int dbg, int role, uint32_t tl, int ev) {
     }
 }
 
-// per FFT bin k: {w0, w1, bits(nf), bits(m_lo)}: weights into filters m_lo[k], m_lo[k]+1, and how many
-// filters complete (nf = m_lo[k] - m_lo[k-1] in {0,1,2}) before bin k is accumulated
-__constant__ float4 c_mel[kBins];
+
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -325,9 +324,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
         const int half = warp >= 8 ? 1 : 0;
         const int wq = warp & 3;                   // TMEM lane quarter == warp % 4
         const int row = wq * 32 + lane;
-        const int ms = __float_as_int(c_mel[kSplit].w);
-        const int cb0 = half ? kSplit : 0, cb1 = half ? kNpad : kSplit;
-        const int cur0 = half ? ms : 0;
+        constexpr int ms = LA_MEL_MS;
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
             const ClipDesc c = p.clips[p.tile_clip[tile]];
@@ -339,58 +336,63 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             const bool valid = f < c.n_frames;
             const int64_t ostride = c.out_stride;
             float* outp = p.out + c.out_off + f;
-            float* optr = outp + cur0 * ostride;    // where the filter held in a0 will be stored
+            float* optr = outp + (half ? ms : 0) * ostride;   // where the filter held in a0 will be stored
             float mx = 0.f;
-            int cur = cur0;
             float a0 = 0.f, a1 = 0.f;
-            auto flush = [&]() {                    // filter `cur` is complete: store its power
+            auto flush = [&]() {                    // the filter held in a0 is complete: store its power
                 if (valid) { *optr = a0; mx = fmaxf(mx, a0); }   // rows past the clip's last frame hold garbage
                 optr += ostride;
-                a0 = a1; a1 = 0.f; ++cur;
+                a0 = a1; a1 = 0.f;
             };
             const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
-            if (p.dbg & 1) {
+            uint32_t re[16], im[16];
+            auto release_tmem = [&]() {             // this warp's share of TMEM is in registers
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty);
+            };
+            // Straight-line code: the filterbank is a compile-time table (la_mel_table.inc), so the
+            // weights are FFMA immediates and the flush points are static. The first bin of each
+            // half never flushes (the accumulators start empty on that filter).
+#define LA_BIN(K, LO, W0, W1, NF)                                                                 \
+            {                                                                                     \
+                const float xr = __uint_as_float(re[(K) & 15]), xi = __uint_as_float(im[(K) & 15]); \
+                const float pw = xr * xr + xi * xi;                                               \
+                if ((NF) >= 1 && (K) != 0 && (K) != kSplit) flush();                              \
+                if ((NF) >= 2 && (K) != 0 && (K) != kSplit) flush();                              \
+                a0 = fmaf(W0, pw, a0);                                                            \
+                a1 = fmaf(W1, pw, a1);                                                            \
+            }
+#define LA_CHUNK(C, LAST)                                                                         \
+            {                                                                                     \
+                tmem_ld16(lane_base + 16 * (C), re);                                              \
+                tmem_ld16(lane_base + kNpad + 16 * (C), im);                                      \
+                tmem_ld_wait();                                                                   \
+                if (LAST) release_tmem();                                                         \
+                LA_MEL_CHUNK_##C(LA_BIN)                                                          \
+            }
+            if (p.dbg & 1) {
+                release_tmem();
                 continue;
             }
-#pragma unroll 1
-            for (int cb = cb0; cb < cb1; cb += 16) {
-                uint32_t re[16], im[16];
-                tmem_ld16(lane_base + cb, re);
-                tmem_ld16(lane_base + kNpad + cb, im);
-                tmem_ld_wait();
-                if (cb + 16 >= cb1) {                   // this warp's share of TMEM is in registers
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty);
-                }
+            if (!half) {
+                LA_CHUNK(0, false) LA_CHUNK(1, false) LA_CHUNK(2, false)
+                LA_CHUNK(3, false) LA_CHUNK(4, false) LA_CHUNK(5, true)
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int k = cb + q;
-                    if (k < kBins) {                    // false only for the 7 padding columns
-                        const float4 mw = c_mel[k];     // warp-uniform constant load
-                        const float xr = __uint_as_float(re[q]), xi = __uint_as_float(im[q]);
-                        const float pw = xr * xr + xi * xi;
-                        const int nf = (q == 0 && cb == cb0) ? 0 : __float_as_int(mw.z);
-                        if (nf > 0) {
-                            flush();
-                            if (nf > 1) flush();
-                        }
-                        a0 = fmaf(mw.x, pw, a0);
-                        a1 = fmaf(mw.y, pw, a1);
-                    }
-                }
+                for (int i = 0; i < LA_MEL_TAIL0; ++i) flush();
+            } else {
+                LA_CHUNK(6, false) LA_CHUNK(7, false) LA_CHUNK(8, false) LA_CHUNK(9, false)
+                LA_CHUNK(10, false) LA_CHUNK(11, false) LA_CHUNK(12, true)
+#pragma unroll
+                for (int i = 0; i < LA_MEL_TAIL1; ++i) flush();
             }
+#undef LA_CHUNK
+#undef LA_BIN
+            if ((warp == 4 || warp == 8) && lane == 0) trace(p.dbg, 2, tl, warp == 4 ? 3 : 6);
             // Filters ms and ms + 1 are fed from both halves: the high half stores its partial
             // sums like any other filter, the low half adds its own after the barrier.
-            if (!half) {
-                while (cur < ms) flush();
-            } else {
-                while (cur < kMels) flush();
-            }
             named_bar_sync(3, 256);                     // both halves, one barrier instruction
+            if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 4);
             if (!half && valid) {
                 float* o0 = outp + ms * ostride;
                 const float v0 = *o0 + a0, v1 = o0[ostride] + a1;
@@ -448,35 +450,9 @@ static void tf32_split(double v, float* hi, float* lo) {
     *lo = l;
 }
 
-// librosa.filters.mel(sr=16000, n_fft=400, n_mels=80): Slaney scale + Slaney area norm, fp32 out
-static void build_mel(std::vector<float>& W) {
-    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
-    const double logstep = std::log(6.4) / 27.0;
-    auto hz_to_mel = [&](double f) { return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp; };
-    auto mel_to_hz = [&](double m) { return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m; };
-    const double mmax = hz_to_mel(8000.0);
-    std::vector<double> mel_f(kMels + 2);
-    for (int i = 0; i < kMels + 2; ++i) {
-        const double m = (i == kMels + 1) ? mmax : i * (mmax / (kMels + 1));
-        mel_f[i] = mel_to_hz(m);
-    }
-    W.assign((size_t)kMels * kBins, 0.f);
-    for (int i = 0; i < kMels; ++i) {
-        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
-        for (int k = 0; k < kBins; ++k) {
-            const double fr = 8000.0 * k / (kBins - 1);
-            const double lower = -(mel_f[i] - fr) / (mel_f[i + 1] - mel_f[i]);
-            const double upper = (mel_f[i + 2] - fr) / (mel_f[i + 2] - mel_f[i + 1]);
-            const float w = (float)std::max(0.0, std::min(lower, upper));
-            W[(size_t)i * kBins + k] = (float)((double)w * enorm);
-        }
-    }
-}
-
 struct LogmelTables {
     std::mutex mu;
     float* d_basis[64] = {nullptr};
-    bool const_done[64] = {false};
 };
 static LogmelTables g_tab;
 
@@ -511,34 +487,6 @@ static cudaError_t ensure_tables(int device, const float** basis_out) {
         e = cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { cudaFree(d); return e; }
         g_tab.d_basis[device] = d;
-    }
-    if (!g_tab.const_done[device]) {
-        std::vector<float> W;
-        build_mel(W);
-        float4 tab[kBins];
-        int prev = 0;
-        for (int k = 0; k < kBins; ++k) {
-            int first = -1;
-            for (int m = 0; m < kMels; ++m)
-                if (W[(size_t)m * kBins + k] != 0.f) { first = m; break; }
-            float w0 = 0.f, w1 = 0.f;
-            int lo = prev;
-            if (first >= 0) {
-                lo = first;
-                w0 = W[(size_t)first * kBins + k];
-                w1 = first + 1 < kMels ? W[(size_t)(first + 1) * kBins + k] : 0.f;
-            }
-            const int nf = k == 0 ? 0 : lo - prev;
-            if (nf < 0 || nf > 2) return cudaErrorInvalidValue;     // the epilogue flushes at most twice per bin
-            float fnf, flo;
-            memcpy(&fnf, &nf, 4);
-            memcpy(&flo, &lo, 4);
-            tab[k] = make_float4(w0, w1, fnf, flo);
-            prev = lo;
-        }
-        cudaError_t e = cudaMemcpyToSymbol(c_mel, tab, sizeof(tab));
-        if (e != cudaSuccess) return e;
-        g_tab.const_done[device] = true;
     }
     *basis_out = g_tab.d_basis[device];
     return cudaSuccess;

@@ -146,3 +146,29 @@ def test_logmel_fp32_formulation_close_to_fp64():
     y = log_mel_spectrogram_torch_f32(a).numpy()
     assert x.shape == (2, 80, 50)
     np.testing.assert_allclose(x, y, atol=1e-4 / 4)   # 1e-4 in log10 domain == 2.5e-5 after /4
+
+
+def test_generated_mel_table_matches_oracle_filterbank():
+    """lyricalignment_b200/csrc/la_mel_table.inc (compile-time literals of the K1 epilogue) must be
+    the oracle's (== librosa's == whisper's) 80 x 201 filterbank, bit for bit."""
+    import re
+    from conftest import ROOT
+    txt = open(os.path.join(ROOT, "lyricalignment_b200", "csrc", "la_mel_table.inc")).read()
+    rows = re.findall(r"X\((\d+), (\d+), (\S+?)f, (\S+?)f, (\d+)\)", txt)
+    assert len(rows) == 201
+    W = oracle.mel_filterbank()
+    rebuilt = np.zeros_like(W)
+    prev = 0
+    for k, lo, w0, w1, nf in rows:
+        k, lo, nf = int(k), int(lo), int(nf)
+        assert nf == (0 if k == 0 else lo - prev) and 0 <= nf <= 2
+        rebuilt[lo, k] = np.float32(float.fromhex(w0))
+        if lo + 1 < 80:
+            rebuilt[lo + 1, k] = np.float32(float.fromhex(w1))
+        else:
+            assert float.fromhex(w1) == 0.0
+        prev = lo
+    assert np.array_equal(rebuilt, W)
+    ms = int(re.search(r"#define LA_MEL_MS (\d+)", txt).group(1))
+    split = int(re.search(r"#define LA_MEL_SPLIT (\d+)", txt).group(1))
+    assert ms == int(rows[split][1])
