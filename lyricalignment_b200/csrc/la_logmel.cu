@@ -190,23 +190,27 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
 
     if (warp == 0) {
         // =============================== producer ==========================================
-        if (lane == 0) {
-            uint32_t it = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
-                const ClipDesc c = p.clips[p.tile_clip[tile]];
-                const int f0 = (tile - c.tile0) * kTileM;
-                const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
-                const bool interior = j0 >= 0 && j0 + kRawRows * kHop <= c.n_samples && (c.wave_off & 3) == 0;
-                mbar_wait(raw_empty, (tl & 1) ^ 1);
+        // All 32 lanes issue the 130 waveform-row copies (a single lane needs ~4 us for them);
+        // lane 0 alone feeds the basis ring.
+        uint32_t it = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
+            const ClipDesc c = p.clips[p.tile_clip[tile]];
+            const int f0 = (tile - c.tile0) * kTileM;
+            const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
+            const bool interior = j0 >= 0 && j0 + kRawRows * kHop <= c.n_samples && (c.wave_off & 3) == 0;
+            mbar_wait(raw_empty, (tl & 1) ^ 1);
+            if (lane == 0) {
                 trace(p.dbg, 3, tl, 0);
-                if (interior) {
-                    mbar_arrive_expect_tx(raw_full, kRawRows * kHop * 4);
-                    const float* src = p.wave + c.wave_off + j0;
-                    for (int h = 0; h < kRawRows; ++h)
-                        bulk_g2s(raw + h * kRawPitch, src + h * kHop, kHop * 4, raw_full);
-                } else {
-                    mbar_arrive(raw_full);             // the transform warps stage boundary tiles themselves
-                }
+                if (interior) mbar_arrive_expect_tx(raw_full, kRawRows * kHop * 4);
+                else mbar_arrive(raw_full);            // the transform warps stage boundary tiles themselves
+            }
+            __syncwarp();
+            if (interior) {
+                const float* src = p.wave + c.wave_off + j0;
+                for (int h = lane; h < kRawRows; h += 32)
+                    bulk_g2s(raw + h * kRawPitch, src + h * kHop, kHop * 4, raw_full);
+            }
+            if (lane == 0) {
                 trace(p.dbg, 3, tl, 1);
                 for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                     const int s = it % kStages;
@@ -219,6 +223,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                              &full[s]);
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ========================================
