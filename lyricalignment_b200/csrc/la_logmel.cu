@@ -48,20 +48,22 @@ constexpr int kTileM = 128;                 // frames per tile
 constexpr int kNpad = 208;                  // 201 bins padded to a multiple of 16
 constexpr int kKSteps = 25;                 // 200 folded samples / 8 (UMMA_K for tf32)
 constexpr int kRawRows = 130;               // hop rows staged per tile
-constexpr int kRawPitch = 164;              // floats; 8 rows x 4 cols hit 32 distinct banks
-constexpr int kALbo = 2064;                 // bytes between K-adjacent core matrices of A (16 * 128 + 16 pad)
-constexpr int kABytes = 2 * kALbo;          // one A operand (hi or lo) of one k-step
-constexpr int kBLbo = (kNpad / 8) * 128;    // 3328
-constexpr int kBBytes = 2 * kBLbo;          // 6656: one B operand (hi or lo) of one k-step
-constexpr int kStageBytes = 4 * kABytes + 4 * kBBytes;   // 43136: [Ae_hi Ae_lo Ao_hi Ao_lo | C_hi C_lo S_hi S_lo]
-constexpr int kStages = 3;
-constexpr int kRawBytes = kRawRows * kRawPitch * 4;   // 85280
+constexpr int kRawGroup = 8;                // hop rows per bulk copy (the TMA request rate, ~35 ns each, is the limit)
+constexpr int kRawGroupPitch = kRawGroup * kHop + 8;   // floats: +8 per group -> thread-per-row reads hit 32 banks
+constexpr int kRawGroups = (kRawRows + kRawGroup - 1) / kRawGroup;   // 17
+constexpr int kRawBytes = kRawGroups * kRawGroupPitch * 4;           // 87584
+constexpr int kBLbo = (kNpad / 8) * 128;    // 3328 bytes between K-adjacent core matrices of the basis
+constexpr int kBBytes = 2 * kBLbo;          // 6656: one basis operand (hi or lo) of one k-step
+constexpr int kBStageBytes = 4 * kBBytes;   // 26624: [C_hi C_lo S_hi S_lo]
+constexpr int kBStages = 5;
+constexpr int kAStages = 3;                 // A operands live in TMEM: 4 planes x 8 columns per stage
+constexpr int kACol0 = 2 * kNpad;           // TMEM columns [0,416) accumulators, [416,512) A ring
 constexpr int kXformWarps = 8;              // warps 12..19
 constexpr int kEpiWarps = 8;                // warps 4..11: two per TMEM lane quarter, bins split at kSplit
 constexpr int kSplit = LA_MEL_SPLIT;        // bins [0, 96) -> warps 4..7, [96, 201) -> warps 8..11
 constexpr int kLogmelThreads = 640;
 constexpr uint32_t kTmemCols = 512;
-static_assert(kStageBytes % 128 == 0, "stage pitch");
+static_assert(kACol0 + kAStages * 32 <= 512, "TMEM columns");
 
 struct ClipDesc {
     int64_t wave_off;   // float offset of the clip's first sample
@@ -119,6 +121,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from TMEM (128 lanes x 8 columns of tf32), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -161,12 +181,14 @@ __device__ __forceinline__ float rna_tf32(float x) {      // round-to-nearest TF
 
 __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* stages = smem;
-    float* raw = reinterpret_cast<float*>(smem + kStages * kStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kRawBytes);
-    uint64_t* full = bars;                    // [kStages] basis landed (tx) + 8 transform warps
-    uint64_t* empty = bars + kStages;         // [kStages] MMAs of the stage retired
-    uint64_t* raw_full = bars + 2 * kStages;
+    unsigned char* bstages = smem;
+    float* raw = reinterpret_cast<float*>(smem + kBStages * kBStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBStages * kBStageBytes + kRawBytes);
+    uint64_t* b_full = bars;                         // [kBStages] basis block landed (tx)
+    uint64_t* b_empty = b_full + kBStages;           // [kBStages] MMAs that read it retired
+    uint64_t* a_full = b_empty + kBStages;           // [kAStages] 8 transform warps stored their planes
+    uint64_t* a_empty = a_full + kAStages;           // [kAStages] MMAs that read it retired
+    uint64_t* raw_full = a_empty + kAStages;
     uint64_t* raw_empty = raw_full + 1;
     uint64_t* tmem_full = raw_full + 2;
     uint64_t* tmem_empty = raw_full + 3;
@@ -175,7 +197,8 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1 + kXformWarps); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&a_full[s], kXformWarps); mbar_init(&a_empty[s], 1); }
         mbar_init(raw_full, 1);
         mbar_init(raw_empty, kXformWarps);
         mbar_init(tmem_full, 1);
@@ -190,40 +213,37 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
 
     if (warp == 0) {
         // =============================== producer ==========================================
-        // All 32 lanes issue the 130 waveform-row copies (a single lane needs ~4 us for them);
-        // lane 0 alone feeds the basis ring.
-        uint32_t it = 0, tl = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
-            const ClipDesc c = p.clips[p.tile_clip[tile]];
-            const int f0 = (tile - c.tile0) * kTileM;
-            const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
-            const bool interior = j0 >= 0 && j0 + kRawRows * kHop <= c.n_samples && (c.wave_off & 3) == 0;
-            mbar_wait(raw_empty, (tl & 1) ^ 1);
-            if (lane == 0) {
+        if (lane == 0) {
+            uint32_t it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
+                const ClipDesc c = p.clips[p.tile_clip[tile]];
+                const int f0 = (tile - c.tile0) * kTileM;
+                const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
+                const bool interior = j0 >= 0 && j0 + kRawRows * kHop <= c.n_samples && (c.wave_off & 3) == 0;
+                mbar_wait(raw_empty, (tl & 1) ^ 1);
                 trace(p.dbg, 3, tl, 0);
-                if (interior) mbar_arrive_expect_tx(raw_full, kRawRows * kHop * 4);
-                else mbar_arrive(raw_full);            // the transform warps stage boundary tiles themselves
-            }
-            __syncwarp();
-            if (interior) {
-                const float* src = p.wave + c.wave_off + j0;
-                for (int h = lane; h < kRawRows; h += 32)
-                    bulk_g2s(raw + h * kRawPitch, src + h * kHop, kHop * 4, raw_full);
-            }
-            if (lane == 0) {
+                if (interior) {
+                    mbar_arrive_expect_tx(raw_full, kRawRows * kHop * 4);
+                    const float* src = p.wave + c.wave_off + j0;
+                    for (int g = 0; g < kRawGroups; ++g) {
+                        const int rows = min(kRawGroup, kRawRows - g * kRawGroup);
+                        bulk_g2s(raw + g * kRawGroupPitch, src + g * kRawGroup * kHop, rows * kHop * 4, raw_full);
+                    }
+                } else {
+                    mbar_arrive(raw_full);             // the transform warps stage boundary tiles themselves
+                }
                 trace(p.dbg, 3, tl, 1);
                 for (int ks = 0; ks < kKSteps; ++ks, ++it) {
-                    const int s = it % kStages;
-                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    const int s = it % kBStages;
+                    mbar_wait(&b_empty[s], ((it / kBStages) & 1) ^ 1);
                     trace(p.dbg, 3, tl, 2 + ks);
-                    if (p.dbg & 4) { mbar_arrive(&full[s]); continue; }
-                    mbar_arrive_expect_tx(&full[s], 4 * kBBytes);
-                    bulk_g2s(stages + s * kStageBytes + 4 * kABytes,
-                             reinterpret_cast<const unsigned char*>(p.basis) + (size_t)ks * 4 * kBBytes, 4 * kBBytes,
-                             &full[s]);
+                    if (p.dbg & 4) { mbar_arrive(&b_full[s]); continue; }
+                    mbar_arrive_expect_tx(&b_full[s], kBStageBytes);
+                    bulk_g2s(bstages + s * kBStageBytes,
+                             reinterpret_cast<const unsigned char*>(p.basis) + (size_t)ks * kBStageBytes, kBStageBytes,
+                             &b_full[s]);
                 }
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ========================================
@@ -234,34 +254,48 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 tc_fence_after();
                 trace(p.dbg, 0, tl, 0);
                 for (int ks = 0; ks < kKSteps; ++ks, ++it) {
-                    const int s = it % kStages;
-                    mbar_wait(&full[s], (it / kStages) & 1);
+                    const int sb = it % kBStages, sa = it % kAStages;
+                    mbar_wait(&a_full[sa], (it / kAStages) & 1);
+                    mbar_wait(&b_full[sb], (it / kBStages) & 1);
                     tc_fence_after();
                     trace(p.dbg, 0, tl, 1 + ks);
-                    const uint32_t sa = smem_u32(stages + s * kStageBytes);
-                    const uint32_t sb = sa + 4 * kABytes;
-                    const uint64_t ae_hi = umma_desc(sa, kALbo, 128), ae_lo = umma_desc(sa + kABytes, kALbo, 128);
-                    const uint64_t ao_hi = umma_desc(sa + 2 * kABytes, kALbo, 128), ao_lo = umma_desc(sa + 3 * kABytes, kALbo, 128);
-                    const uint64_t c_hi = umma_desc(sb, kBLbo, 128), c_lo = umma_desc(sb + kBBytes, kBLbo, 128);
-                    const uint64_t s_hi = umma_desc(sb + 2 * kBBytes, kBLbo, 128), s_lo = umma_desc(sb + 3 * kBBytes, kBLbo, 128);
+                    const uint32_t ta = tmem_base + kACol0 + sa * 32;     // e_hi, e_lo, o_hi, o_lo: 8 columns each
+                    const uint32_t sbs = smem_u32(bstages + sb * kBStageBytes);
+                    const uint64_t c_hi = umma_desc(sbs, kBLbo, 128), c_lo = umma_desc(sbs + kBBytes, kBLbo, 128);
+                    const uint64_t s_hi = umma_desc(sbs + 2 * kBBytes, kBLbo, 128), s_lo = umma_desc(sbs + 3 * kBBytes, kBLbo, 128);
                     const uint32_t acc = ks > 0 ? 1u : 0u;
-                    umma_tf32(tmem_base, ae_hi, c_lo, kIdesc, acc);           // Re: small terms first
-                    umma_tf32(tmem_base, ae_lo, c_hi, kIdesc, 1u);
-                    umma_tf32(tmem_base, ae_hi, c_hi, kIdesc, 1u);
-                    umma_tf32(tmem_base + kNpad, ao_hi, s_lo, kIdesc, acc);   // Im
-                    umma_tf32(tmem_base + kNpad, ao_lo, s_hi, kIdesc, 1u);
-                    umma_tf32(tmem_base + kNpad, ao_hi, s_hi, kIdesc, 1u);
-                    umma_commit(&empty[s]);
+                    umma_tf32_ts(tmem_base, ta, c_lo, kIdesc, acc);                 // Re: small terms first
+                    umma_tf32_ts(tmem_base, ta + 8, c_hi, kIdesc, 1u);
+                    umma_tf32_ts(tmem_base, ta, c_hi, kIdesc, 1u);
+                    umma_tf32_ts(tmem_base + kNpad, ta + 16, s_lo, kIdesc, acc);    // Im
+                    umma_tf32_ts(tmem_base + kNpad, ta + 24, s_hi, kIdesc, 1u);
+                    umma_tf32_ts(tmem_base + kNpad, ta + 16, s_hi, kIdesc, 1u);
+                    umma_commit(&a_empty[sa]);
+                    umma_commit(&b_empty[sb]);
                 }
                 umma_commit(tmem_full);
                 trace(p.dbg, 0, tl, 26);
             }
         }
     } else if (warp >= 12) {
-        // ====================== transform: staged waveform -> A operands (256 threads) =======
-        const int tw = warp - 12;
+        // ====================== transform: staged waveform -> A operands in TMEM =============
+        // Thread = frame row (TMEM lane). Warps 12..15 produce the even planes (x[n] + x[400-n]),
+        // warps 16..19 the odd ones (x[n] - x[400-n]); both split hi/lo and tcgen05.st 8 columns
+        // per plane. Sample s of the tile sits at raw[s + 8 * (s / 1280)] (8 hop rows per bulk
+        // copy, 8 floats of padding between copies). Lane l reads its 8 samples rotated by l & 7,
+        // which makes every LDS hit 32 distinct banks; three select stages undo the rotation.
+        const bool odd = warp >= 16;
+        const int q = warp & 3;                    // TMEM lane quarter == warp % 4
+        const int r = q * 32 + lane;
         const int xt = tid - 384;
-        const int rsub = lane >> 2, kq = lane & 3;
+        const int rot = lane & 7;
+        int jj[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) jj[j] = (j + rot) & 7;
+        const float* row_d0 = raw + r * kHop + 8 * (r >> 3);          // hop-row offset 0, 1, 2 of frame r
+        const float* row_d1 = raw + r * kHop + 8 * ((r + 1) >> 3);
+        const float* row_d2 = raw + r * kHop + 8 * ((r + 2) >> 3);
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + kACol0 + (odd ? 16 : 0);
         uint32_t it = 0, tl = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
             const ClipDesc c = p.clips[p.tile_clip[tile]];
@@ -280,40 +314,47 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                     if (j < 0) j = -j;
                     if (j >= N) j = 2 * (int64_t)(N - 1) - j;
                     j = j < 0 ? 0 : (j >= N ? N - 1 : j);
-                    raw[(idx / kHop) * kRawPitch + idx % kHop] = __ldg(x + j);
+                    raw[idx + 8 * (idx / (kRawGroup * kHop))] = __ldg(x + j);
                 }
                 named_bar_sync(2, 256);
             }
-            // sample s = r*160 + n of the tile sits at raw[r*164 + n + 4*(n/160)]
             for (int ks = 0; ks < kKSteps; ++ks, ++it) {
-                const int s = it % kStages;
-                mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                const int sa = it % kAStages;
+                mbar_wait(&a_empty[sa], ((it / kAStages) & 1) ^ 1);
+                tc_fence_after();
                 if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 1 + ks);
-                unsigned char* st = stages + s * kStageBytes;
-                if (!(p.dbg & 2))
+                float v[8];
+                if (!(p.dbg & 2)) {
+                    const int n0 = ks * 8 + 1;                           // n = n0 + jj in 1..200
+                    const float* rev_row = (kNfft - n0 - 7 >= 2 * kHop) ? row_d2 : row_d1;   // m = 400 - n: 8-aligned windows never straddle 320
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int r = tw * 16 + g * 8 + rsub;
-                    const float* rrow = raw + r * kRawPitch;
-#pragma unroll
-                    for (int ki = 0; ki < 2; ++ki) {
-                        const int n = ks * 8 + ki * 4 + kq + 1;              // 1..200
-                        const int m = kNfft - n;                             // 200..399
-                        const float fwd = rrow[n + (n >= kHop ? 4 : 0)];
-                        const float rev = rrow[m + 4 + (m >= 2 * kHop ? 4 : 0)];
-                        const float e = fwd + rev, o = fwd - rev;            // n = 200: e = 2 x[200] (basis row halved), o = 0
-                        const float e_hi = rna_tf32(e), o_hi = rna_tf32(o);
-                        const float e_lo = rna_tf32(e - e_hi), o_lo = rna_tf32(o - o_hi);
-                        const int off = ki * kALbo + (r >> 3) * 128 + (r & 7) * 16 + kq * 4;
-                        *reinterpret_cast<float*>(st + off) = e_hi;
-                        *reinterpret_cast<float*>(st + kABytes + off) = e_lo;
-                        *reinterpret_cast<float*>(st + 2 * kABytes + off) = o_hi;
-                        *reinterpret_cast<float*>(st + 3 * kABytes + off) = o_lo;
+                    for (int j = 0; j < 8; ++j) {
+                        const int n = n0 + jj[j];
+                        const float fwd = (n >= kHop ? row_d1 : row_d0)[n];
+                        const float rev = rev_row[kNfft - n];
+                        v[j] = odd ? fwd - rev : fwd + rev;              // n = 200: e = 2 x[200] (basis row halved), o = 0
                     }
+                    // undo the rotation: w[c] = v[(c - rot) & 7]
+                    float t[8];
+#pragma unroll
+                    for (int cidx = 0; cidx < 8; ++cidx) t[cidx] = (rot & 1) ? v[(cidx + 7) & 7] : v[cidx];
+#pragma unroll
+                    for (int cidx = 0; cidx < 8; ++cidx) v[cidx] = (rot & 2) ? t[(cidx + 6) & 7] : t[cidx];
+#pragma unroll
+                    for (int cidx = 0; cidx < 8; ++cidx) t[cidx] = (rot & 4) ? v[(cidx + 4) & 7] : v[cidx];
+                    float hi[8], lo[8];
+#pragma unroll
+                    for (int cidx = 0; cidx < 8; ++cidx) {
+                        hi[cidx] = rna_tf32(t[cidx]);
+                        lo[cidx] = rna_tf32(t[cidx] - hi[cidx]);
+                    }
+                    tmem_st8(tlane + sa * 32, hi);
+                    tmem_st8(tlane + sa * 32 + 8, lo);
+                    tmem_st_wait();
                 }
-                fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core
+                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
+                if (lane == 0) mbar_arrive(&a_full[sa]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(raw_empty);      // staged waveform no longer needed
@@ -497,7 +538,7 @@ static cudaError_t ensure_tables(int device, const float** basis_out) {
     return cudaSuccess;
 }
 
-size_t logmel_smem_bytes() { return (size_t)kStages * kStageBytes + kRawBytes + 128; }
+size_t logmel_smem_bytes() { return (size_t)kBStages * kBStageBytes + kRawBytes + 256; }
 
 }  // namespace la
 
