@@ -58,10 +58,10 @@ constexpr int kBStageBytes = 4 * kBBytes;   // 26624: [C_hi C_lo S_hi S_lo]
 constexpr int kBStages = 5;
 constexpr int kAStages = 3;                 // A operands live in TMEM: 4 planes x 8 columns per stage
 constexpr int kACol0 = 2 * kNpad;           // TMEM columns [0,416) accumulators, [416,512) A ring
-constexpr int kXformWarps = 8;              // warps 12..19
+constexpr int kXformWarps = 16;             // warps 12..27: {even,odd k-steps} x {even,odd planes} x 4 lane quarters
 constexpr int kEpiWarps = 8;                // warps 4..11: two per TMEM lane quarter, bins split at kSplit
 constexpr int kSplit = LA_MEL_SPLIT;        // bins [0, 96) -> warps 4..7, [96, 201) -> warps 8..11
-constexpr int kLogmelThreads = 640;
+constexpr int kLogmelThreads = 896;
 constexpr uint32_t kTmemCols = 512;
 static_assert(kACol0 + kAStages * 32 <= 512, "TMEM columns");
 
@@ -179,6 +179,19 @@ __device__ __forceinline__ float rna_tf32(float x) {      // round-to-nearest TF
     return __uint_as_float(r);
 }
 
+// How hop-row group g (8 rows = 1280 samples) of a tile is staged: 0 = not needed (feeds only frames
+// past the clip end), 1 = one TMA bulk copy, 2 = plain loads with reflect padding (clip edges).
+__device__ __forceinline__ int raw_group_mode(const ClipDesc& c, int64_t j0, int f0, int g) {
+    const int64_t a = j0 + (int64_t)g * kRawGroup * kHop;
+    const int rows = min(kRawGroup, kRawRows - g * kRawGroup);
+    const int64_t b = a + rows * kHop;                       // samples [a, b)
+    const int last_valid = min(kTileM, c.n_frames - f0) - 1; // last frame row of the tile that is stored
+    const int64_t need_hi = j0 + (int64_t)last_valid * kHop + kNfft;   // exclusive
+    if (a >= need_hi) return 0;
+    if (a >= 0 && b <= c.n_samples && (c.wave_off & 3) == 0) return 1;
+    return 2;
+}
+
 __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* bstages = smem;
@@ -198,7 +211,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
 
     if (tid == 0) {
         for (int s = 0; s < kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&a_full[s], kXformWarps); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&a_full[s], kXformWarps / 2); mbar_init(&a_empty[s], 1); }
         mbar_init(raw_full, 1);
         mbar_init(raw_empty, kXformWarps);
         mbar_init(tmem_full, 1);
@@ -219,19 +232,18 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 const ClipDesc c = p.clips[p.tile_clip[tile]];
                 const int f0 = (tile - c.tile0) * kTileM;
                 const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
-                const bool interior = j0 >= 0 && j0 + kRawRows * kHop <= c.n_samples && (c.wave_off & 3) == 0;
                 mbar_wait(raw_empty, (tl & 1) ^ 1);
                 trace(p.dbg, 3, tl, 0);
-                if (interior) {
-                    mbar_arrive_expect_tx(raw_full, kRawRows * kHop * 4);
-                    const float* src = p.wave + c.wave_off + j0;
-                    for (int g = 0; g < kRawGroups; ++g) {
-                        const int rows = min(kRawGroup, kRawRows - g * kRawGroup);
-                        bulk_g2s(raw + g * kRawGroupPitch, src + g * kRawGroup * kHop, rows * kHop * 4, raw_full);
-                    }
-                } else {
-                    mbar_arrive(raw_full);             // the transform warps stage boundary tiles themselves
-                }
+                uint32_t tx = 0;
+                for (int g = 0; g < kRawGroups; ++g)
+                    if (raw_group_mode(c, j0, f0, g) == 1) tx += min(kRawGroup, kRawRows - g * kRawGroup) * kHop * 4;
+                if (tx) mbar_arrive_expect_tx(raw_full, tx);
+                else mbar_arrive(raw_full);
+                const float* src = p.wave + c.wave_off + j0;
+                for (int g = 0; g < kRawGroups; ++g)
+                    if (raw_group_mode(c, j0, f0, g) == 1)
+                        bulk_g2s(raw + g * kRawGroupPitch, src + g * kRawGroup * kHop,
+                                 min(kRawGroup, kRawRows - g * kRawGroup) * kHop * 4, raw_full);
                 trace(p.dbg, 3, tl, 1);
                 for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                     const int s = it % kBStages;
@@ -284,7 +296,8 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
         // per plane. Sample s of the tile sits at raw[s + 8 * (s / 1280)] (8 hop rows per bulk
         // copy, 8 floats of padding between copies). Lane l reads its 8 samples rotated by l & 7,
         // which makes every LDS hit 32 distinct banks; three select stages undo the rotation.
-        const bool odd = warp >= 16;
+        const bool odd = (warp - 12) & 4;          // warps 12-15, 20-23: even planes; 16-19, 24-27: odd planes
+        const int kpar = warp >= 20 ? 1 : 0;       // which k-steps this warp serves (two warp sets ping-pong)
         const int q = warp & 3;                    // TMEM lane quarter == warp % 4
         const int r = q * 32 + lane;
         const int xt = tid - 384;
@@ -296,35 +309,38 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
         const float* row_d1 = raw + r * kHop + 8 * ((r + 1) >> 3);
         const float* row_d2 = raw + r * kHop + 8 * ((r + 2) >> 3);
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + kACol0 + (odd ? 16 : 0);
-        uint32_t it = 0, tl = 0;
+        uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
             const ClipDesc c = p.clips[p.tile_clip[tile]];
             const int f0 = (tile - c.tile0) * kTileM;
             const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
-            const bool interior = j0 >= 0 && j0 + kRawRows * kHop <= c.n_samples && (c.wave_off & 3) == 0;
             mbar_wait(raw_full, tl & 1);
             if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 0);
-            if (!interior) {
-                // reflect padding (torch.stft centre=True) and ragged clip ends, by plain loads
+            {
+                // clip edges: reflect padding (torch.stft centre=True) / ragged ends, by plain loads
+                bool any = false;
                 const float* x = p.wave + c.wave_off;
                 const int N = c.n_samples;
-#pragma unroll 4
-                for (int idx = xt; idx < kRawRows * kHop; idx += 256) {
-                    int64_t j = j0 + idx;
-                    if (j < 0) j = -j;
-                    if (j >= N) j = 2 * (int64_t)(N - 1) - j;
-                    j = j < 0 ? 0 : (j >= N ? N - 1 : j);
-                    raw[idx + 8 * (idx / (kRawGroup * kHop))] = __ldg(x + j);
+                for (int g = 0; g < kRawGroups; ++g) {
+                    if (raw_group_mode(c, j0, f0, g) != 2) continue;
+                    any = true;
+                    const int cnt = min(kRawGroup, kRawRows - g * kRawGroup) * kHop;
+                    for (int i = xt; i < cnt; i += 512) {
+                        int64_t j = j0 + (int64_t)g * kRawGroup * kHop + i;
+                        if (j < 0) j = -j;
+                        if (j >= N) j = 2 * (int64_t)(N - 1) - j;
+                        j = j < 0 ? 0 : (j >= N ? N - 1 : j);
+                        raw[g * kRawGroupPitch + i] = __ldg(x + j);
+                    }
                 }
-                named_bar_sync(2, 256);
+                if (any) named_bar_sync(2, 512);
             }
-            for (int ks = 0; ks < kKSteps; ++ks, ++it) {
+            for (int ks = kpar; ks < kKSteps; ks += 2) {
+                const uint32_t it = tl * kKSteps + ks;
                 const int sa = it % kAStages;
-                mbar_wait(&a_empty[sa], ((it / kAStages) & 1) ^ 1);
-                tc_fence_after();
-                if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 1 + ks);
-                float v[8];
+                float hi[8], lo[8];
                 if (!(p.dbg & 2)) {
+                    float v[8];
                     const int n0 = ks * 8 + 1;                           // n = n0 + jj in 1..200
                     const float* rev_row = (kNfft - n0 - 7 >= 2 * kHop) ? row_d2 : row_d1;   // m = 400 - n: 8-aligned windows never straddle 320
 #pragma unroll
@@ -342,12 +358,17 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                     for (int cidx = 0; cidx < 8; ++cidx) v[cidx] = (rot & 2) ? t[(cidx + 6) & 7] : t[cidx];
 #pragma unroll
                     for (int cidx = 0; cidx < 8; ++cidx) t[cidx] = (rot & 4) ? v[(cidx + 4) & 7] : v[cidx];
-                    float hi[8], lo[8];
 #pragma unroll
                     for (int cidx = 0; cidx < 8; ++cidx) {
                         hi[cidx] = rna_tf32(t[cidx]);
                         lo[cidx] = rna_tf32(t[cidx] - hi[cidx]);
                     }
+                }
+                // only the stores need the TMEM stage: everything above overlaps the MMAs in flight
+                mbar_wait(&a_empty[sa], ((it / kAStages) & 1) ^ 1);
+                tc_fence_after();
+                if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 1 + ks);
+                if (!(p.dbg & 2)) {
                     tmem_st8(tlane + sa * 32, hi);
                     tmem_st8(tlane + sa * 32 + 8, lo);
                     tmem_st_wait();
@@ -360,7 +381,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             if (lane == 0) mbar_arrive(raw_empty);      // staged waveform no longer needed
             if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 26);
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 12) {
         // ====================== epilogue: power -> mel, straight out of TMEM (256 threads) ====
         // Two warps share each TMEM lane quarter and split the 201 bins at kSplit. Exactly two
         // filters (ms, ms + 1, ms = first filter fed by bin kSplit) receive power from both sides.
