@@ -16,18 +16,25 @@
 // (the dropped lo*lo term is 2^-22 relative), which lands 1e-6..1e-5 from the fp64 oracle in
 // the log10 domain (single-pass TF32 would be 3e-1 off on tonal input).
 //
-// One persistent CTA per SM, 128-frame tiles, warp-specialised:
-//   warp 0      producer: 1-D TMA bulk copies of the tile's waveform rows (130 hop rows of 640 B
-//               into a 656 B-pitch, bank-conflict-free staging area) and of the constant basis
-//               blocks (26 KB per k-step, L2-resident) into a 3-deep ring;
-//   warp 1      TMEM allocator + MMA issuer (one elected lane, 150 tcgen05.mma per tile);
-//   warps 12..19 transform: staged waveform -> folded, hi/lo-split A operands in the UMMA
-//               canonical no-swizzle K-major layout (bank-conflict-free both ways);
-//   warps 4..11 epilogue (two warps per TMEM lane quarter, bins split in two): TMEM ->
-//               registers, power, sparse mel projection (each FFT bin feeds <= 2 adjacent
-//               triangular filters), coalesced stores of the mel power, running max.
-// Clip-boundary tiles (reflect padding, ragged ends) are staged by the transform warps with
-// plain loads instead of TMA. A second small kernel applies log10, the max-8 floor and (x+4)/4.
+// One persistent CTA per SM (896 threads), 128-frame tiles, warp-specialised:
+//   warp 0       producer: 1-D TMA bulk copies of the tile's waveform (17 copies of 8 hop rows into a
+//                staging area padded by 8 floats per copy) and of the constant basis blocks (26 KB per
+//                k-step, L2-resident) into a 5-deep shared-memory ring;
+//   warps 1, 2   MMA issuers (one elected lane each: Re and Im accumulators, 75 tcgen05.mma per tile
+//                each, A operand from TMEM, B from shared memory); warp 1 also owns the TMEM allocation;
+//   warps 12..27 transform: staged waveform -> folded, hi/lo-split A operands written straight into
+//                TMEM with tcgen05.st (thread = frame row = TMEM lane; bank-conflict-free rotated
+//                reads); two warp sets ping-pong the k-steps through a 3-deep TMEM ring;
+//   warps 4..11  epilogue (two warps per TMEM lane quarter, bins split in two): TMEM -> registers,
+//                power, sparse mel projection as straight-line code from a generated compile-time
+//                table (each FFT bin feeds <= 2 adjacent triangular filters), coalesced stores of the
+//                mel power, running max.
+// TMEM: columns [0,416) hold the Re/Im accumulators, [416,512) the A ring. Clip-edge hop-row groups
+// (reflect padding, ragged ends) are staged by the transform warps with plain loads instead of
+// TMA. A second small kernel applies log10, the max-8 floor and (x+4)/4.
+// History of the tuning (profiles/k1_tuning_r1.md): SS-mode operands were shared-memory-bandwidth
+// bound, a 3200-instruction unrolled epilogue was instruction-fetch bound, a single MMA issuer left
+// the tensor pipe idle ~30 % of the time.
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -179,17 +186,25 @@ __device__ __forceinline__ float rna_tf32(float x) {      // round-to-nearest TF
     return __uint_as_float(r);
 }
 
-// How hop-row group g (8 rows = 1280 samples) of a tile is staged: 0 = not needed (feeds only frames
-// past the clip end), 1 = one TMA bulk copy, 2 = plain loads with reflect padding (clip edges).
-__device__ __forceinline__ int raw_group_mode(const ClipDesc& c, int64_t j0, int f0, int g) {
-    const int64_t a = j0 + (int64_t)g * kRawGroup * kHop;
-    const int rows = min(kRawGroup, kRawRows - g * kRawGroup);
-    const int64_t b = a + rows * kHop;                       // samples [a, b)
-    const int last_valid = min(kTileM, c.n_frames - f0) - 1; // last frame row of the tile that is stored
-    const int64_t need_hi = j0 + (int64_t)last_valid * kHop + kNfft;   // exclusive
-    if (a >= need_hi) return 0;
-    if (a >= 0 && b <= c.n_samples && (c.wave_off & 3) == 0) return 1;
-    return 2;
+// How the hop-row groups (8 rows = 1280 samples each) of a tile are staged. Computed once per tile:
+// groups [0, need) are needed at all (the rest feed only frames past the clip end), of those the
+// groups [lo, hi) lie fully inside the clip and take one TMA bulk copy each, the others (clip
+// edges: reflect padding, ragged end) are filled by plain loads.
+struct RawPlan { int need, lo, hi; };
+__device__ __forceinline__ RawPlan raw_plan(const ClipDesc& c, int64_t j0, int f0) {
+    RawPlan r;
+    const int last_valid = min(kTileM, c.n_frames - f0) - 1;            // last frame row of the tile that is stored
+    const int64_t need_hi = (int64_t)last_valid * kHop + kNfft;         // tile-relative, exclusive
+    r.need = min(kRawGroups, (int)((need_hi + kRawGroup * kHop - 1) / (kRawGroup * kHop)));
+    r.lo = j0 < 0 ? 1 : 0;
+    const int64_t inside = ((int64_t)c.n_samples - j0) / (kRawGroup * kHop);   // groups ending at or before the clip end
+    r.hi = (int)max((int64_t)r.lo, min((int64_t)r.need, inside));
+    if ((c.wave_off & 3) != 0) r.hi = r.lo;                              // unaligned clip: no TMA at all
+    // the last group holds only 2 rows: it is inside iff those 2 rows are
+    if (r.hi == kRawGroups - 1 && r.need == kRawGroups &&
+        j0 + (int64_t)(kRawGroups - 1) * kRawGroup * kHop + (kRawRows - (kRawGroups - 1) * kRawGroup) * kHop <= c.n_samples)
+        r.hi = kRawGroups;
+    return r;
 }
 
 __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelParams p) {
@@ -210,11 +225,11 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&a_full[s], kXformWarps / 2); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2); }      // 2 MMA issuers
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&a_full[s], kXformWarps / 2); mbar_init(&a_empty[s], 2); }
         mbar_init(raw_full, 1);
         mbar_init(raw_empty, kXformWarps);
-        mbar_init(tmem_full, 1);
+        mbar_init(tmem_full, 2);
         mbar_init(tmem_empty, kEpiWarps);
         mbar_fence_init();
     }
@@ -234,16 +249,15 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
                 mbar_wait(raw_empty, (tl & 1) ^ 1);
                 trace(p.dbg, 3, tl, 0);
+                const RawPlan rp = raw_plan(c, j0, f0);
                 uint32_t tx = 0;
-                for (int g = 0; g < kRawGroups; ++g)
-                    if (raw_group_mode(c, j0, f0, g) == 1) tx += min(kRawGroup, kRawRows - g * kRawGroup) * kHop * 4;
+                for (int g = rp.lo; g < rp.hi; ++g) tx += min(kRawGroup, kRawRows - g * kRawGroup) * kHop * 4;
                 if (tx) mbar_arrive_expect_tx(raw_full, tx);
                 else mbar_arrive(raw_full);
                 const float* src = p.wave + c.wave_off + j0;
-                for (int g = 0; g < kRawGroups; ++g)
-                    if (raw_group_mode(c, j0, f0, g) == 1)
-                        bulk_g2s(raw + g * kRawGroupPitch, src + g * kRawGroup * kHop,
-                                 min(kRawGroup, kRawRows - g * kRawGroup) * kHop * 4, raw_full);
+                for (int g = rp.lo; g < rp.hi; ++g)
+                    bulk_g2s(raw + g * kRawGroupPitch, src + g * kRawGroup * kHop,
+                             min(kRawGroup, kRawRows - g * kRawGroup) * kHop * 4, raw_full);
                 trace(p.dbg, 3, tl, 1);
                 for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                     const int s = it % kBStages;
@@ -257,36 +271,41 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 }
             }
         }
-    } else if (warp == 1) {
-        // =============================== MMA issuer ========================================
+    } else if (warp == 1 || warp == 2) {
+        // =============================== MMA issuers =======================================
+        // Two issuing threads: warp 1 accumulates Re (even planes x cos basis), warp 2 Im (odd planes x
+        // sin basis). tcgen05.mma issue is back-pressured by the tensor pipe, so a single issuer's
+        // per-k-step bookkeeping (barrier waits, commits) left the pipe idle ~30 % of the time;
+        // with two, one thread's bookkeeping overlaps the other's MMAs. Each accumulator is written
+        // by one thread in program order, so results stay deterministic.
         if (lane == 0) {
+            const int im = warp == 2 ? 1 : 0;
+            const uint32_t d_acc = tmem_base + (im ? kNpad : 0);
+            const uint32_t ta0 = tmem_base + kACol0 + (im ? 16 : 0);               // hi plane; lo plane at +8
+            const uint64_t bd_hi0 = umma_desc(smem_u32(bstages) + (im ? 2 * kBBytes : 0), kBLbo, 128);
+            const uint64_t bd_lo0 = umma_desc(smem_u32(bstages) + (im ? 3 * kBBytes : kBBytes), kBLbo, 128);
             uint32_t it = 0, tl = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
                 mbar_wait(tmem_empty, (tl & 1) ^ 1);       // epilogue of the previous tile drained TMEM
                 tc_fence_after();
-                trace(p.dbg, 0, tl, 0);
+                if (!im) trace(p.dbg, 0, tl, 0);
                 for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                     const int sb = it % kBStages, sa = it % kAStages;
-                    mbar_wait(&a_full[sa], (it / kAStages) & 1);
                     mbar_wait(&b_full[sb], (it / kBStages) & 1);
+                    mbar_wait(&a_full[sa], (it / kAStages) & 1);
                     tc_fence_after();
-                    trace(p.dbg, 0, tl, 1 + ks);
-                    const uint32_t ta = tmem_base + kACol0 + sa * 32;     // e_hi, e_lo, o_hi, o_lo: 8 columns each
-                    const uint32_t sbs = smem_u32(bstages + sb * kBStageBytes);
-                    const uint64_t c_hi = umma_desc(sbs, kBLbo, 128), c_lo = umma_desc(sbs + kBBytes, kBLbo, 128);
-                    const uint64_t s_hi = umma_desc(sbs + 2 * kBBytes, kBLbo, 128), s_lo = umma_desc(sbs + 3 * kBBytes, kBLbo, 128);
-                    const uint32_t acc = ks > 0 ? 1u : 0u;
-                    umma_tf32_ts(tmem_base, ta, c_lo, kIdesc, acc);                 // Re: small terms first
-                    umma_tf32_ts(tmem_base, ta + 8, c_hi, kIdesc, 1u);
-                    umma_tf32_ts(tmem_base, ta, c_hi, kIdesc, 1u);
-                    umma_tf32_ts(tmem_base + kNpad, ta + 16, s_lo, kIdesc, acc);    // Im
-                    umma_tf32_ts(tmem_base + kNpad, ta + 24, s_hi, kIdesc, 1u);
-                    umma_tf32_ts(tmem_base + kNpad, ta + 16, s_hi, kIdesc, 1u);
+                    if (!im) trace(p.dbg, 0, tl, 1 + ks);
+                    const uint32_t ta = ta0 + sa * 32;
+                    const uint64_t b_hi = bd_hi0 + (uint64_t)(sb * (kBStageBytes >> 4));   // start-address field += stage
+                    const uint64_t b_lo = bd_lo0 + (uint64_t)(sb * (kBStageBytes >> 4));
+                    umma_tf32_ts(d_acc, ta, b_lo, kIdesc, ks > 0 ? 1u : 0u);   // small terms first
+                    umma_tf32_ts(d_acc, ta + 8, b_hi, kIdesc, 1u);
+                    umma_tf32_ts(d_acc, ta, b_hi, kIdesc, 1u);
                     umma_commit(&a_empty[sa]);
                     umma_commit(&b_empty[sb]);
                 }
                 umma_commit(tmem_full);
-                trace(p.dbg, 0, tl, 26);
+                if (!im) trace(p.dbg, 0, tl, 26);
             }
         }
     } else if (warp >= 12) {
@@ -318,12 +337,12 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 0);
             {
                 // clip edges: reflect padding (torch.stft centre=True) / ragged ends, by plain loads
-                bool any = false;
+                const RawPlan rp = raw_plan(c, j0, f0);
+                const bool any = rp.lo > 0 || rp.hi < rp.need;
                 const float* x = p.wave + c.wave_off;
                 const int N = c.n_samples;
-                for (int g = 0; g < kRawGroups; ++g) {
-                    if (raw_group_mode(c, j0, f0, g) != 2) continue;
-                    any = true;
+                for (int g = 0; g < rp.need; ++g) {
+                    if (g >= rp.lo && g < rp.hi) continue;
                     const int cnt = min(kRawGroup, kRawRows - g * kRawGroup) * kHop;
                     for (int i = xt; i < cnt; i += 512) {
                         int64_t j = j0 + (int64_t)g * kRawGroup * kHop + i;

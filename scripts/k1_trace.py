@@ -24,3 +24,8 @@ for tl in range(1, 6):
     print(f" mma: tmem_empty ok {m[0]}, full ok ks0..4 {m[1:6].tolist()} ... ks24 {m[25]}, committed {m[26]}")
     print(f" epi: tmem_full ok {e[0]}, w4 chunks done {e[2]}, w4 flushed {e[3]}, barrier passed {e[4]}, end {e[1]} | w8 chunks done {e[5]}, w8 flushed {e[6]}")
     print(f" per-kstep mma deltas (ns): {np.diff(m[1:26]).tolist()}")
+tl = 3
+m, x, p = t[0, tl] - t0, t[1, tl] - t0, t[3, tl] - t0
+print("ks : mma full-ok | xform(a_empty ok, even ks only) | producer b_empty ok")
+for ks in range(25):
+    print(f"{ks:2d} : {m[1+ks]:7d} | {x[1+ks] if ks % 2 == 0 else -1:7d} | {p[2+ks]:7d}")
