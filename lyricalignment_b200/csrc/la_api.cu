@@ -29,7 +29,19 @@ namespace la {
 int set_error(int code, const char* msg) { return fail(code, msg); }
 }
 
-constexpr int kBuckets = 5;
+// K3 launch shapes: one pair (blank + label state) per lane wherever possible -- the frame step is a
+// dependent chain whose length grows with the pairs a lane owns, so lanes are spent before pairs
+// per lane. Bucket 0: warp per utterance; 1..5: CTA per utterance with 2..32 warps; 6..8: 32 warps
+// with 2/4/8 pairs per lane (L up to 8191).
+constexpr int kBuckets = 9;
+struct BucketShape { int K; int warps; bool wide; };
+static const BucketShape kShape[kBuckets] = {{1, 1, false}, {1, 2, true}, {1, 4, true}, {1, 8, true}, {1, 16, true},
+                                             {1, 32, true}, {2, 32, true}, {4, 32, true}, {8, 32, true}};
+static int bucket_for_pairs(int pairs) {
+    for (int b = 0; b < kBuckets; ++b)
+        if (pairs <= 32 * kShape[b].K * kShape[b].warps) return b;
+    return kBuckets - 1;
+}
 
 struct la_plan {
     int mode = 0, n_utt = 0, V = 0, device = 0, sm_count = 148;
@@ -38,13 +50,12 @@ struct la_plan {
     std::vector<int64_t> e_off, bp_off;     // floats / uint32 words, relative to their area
     size_t emit_bytes = 0, bp_bytes = 0;
     std::vector<int32_t> order[kBuckets];
-    int row_max[kBuckets] = {0, 0, 0, 0, 0};
-    int wide_warps[kBuckets] = {0, 0, 0, 0, 0};
+    int row_max[kBuckets] = {0};
     // device metadata blob
     void* d_meta = nullptr;
     bool meta_pooled = false;
     la::BatchMeta meta{};
-    const int32_t* d_order[kBuckets] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const int32_t* d_order[kBuckets] = {nullptr};
 };
 
 // Host-path context (la_align_host): one per device, grown on demand, reused across plans so a
@@ -150,32 +161,24 @@ int la_plan_create(la_plan** out, int mode, int n_utt, int V, const int32_t* h_t
         if (h_labels[i] < 0 || h_labels[i] >= V) { delete P; return fail(LA_ERR_ARG, "label column out of range"); }
 
     // buckets + workspace layout
-    int wide_need[kBuckets] = {0, 0, 0, 0, 0};
     std::vector<int> bucket_of(n_utt, 0);
     for (int u = 0; u < n_utt; ++u) {
-        const int L = h_l_len[u], pairs = L + 1;
-        int b;
-        if (pairs <= 32) b = 0; else if (pairs <= 64) b = 1; else if (pairs <= 128) b = 2;
-        else if (pairs <= 4096) b = 3; else b = 4;
+        const int L = h_l_len[u];
+        const int b = bucket_for_pairs(L + 1);
         bucket_of[u] = b;
-        const int K = (b == 0) ? 1 : (b == 1) ? 2 : (b == 4) ? 8 : 4;
-        if (b >= 3) wide_need[b] = std::max(wide_need[b], (pairs + 32 * K - 1) / (32 * K));
         P->e_row[u] = (int32_t)align_up((size_t)L + 1, 4);
         P->row_max[b] = std::max(P->row_max[b], P->e_row[u]);
         P->order[b].push_back(u);
     }
     size_t e_floats = 0, bp_words = 0;
     for (int u = 0; u < n_utt; ++u) {
-        const int b = bucket_of[u];
-        const int K = (b == 0) ? 1 : (b == 1) ? 2 : (b == 4) ? 8 : 4;
-        const int threads = (b >= 3) ? 32 * wide_need[b] : 32;
-        P->bp_pairs[u] = threads * K;
+        const BucketShape& sh = kShape[bucket_of[u]];
+        P->bp_pairs[u] = 32 * sh.warps * sh.K;
         P->e_off[u] = (int64_t)e_floats;
         e_floats += (size_t)h_t_len[u] * P->e_row[u];
         P->bp_off[u] = (int64_t)bp_words;
         bp_words += (size_t)((h_t_len[u] + 7) / 8) * P->bp_pairs[u];
     }
-    for (int b = 0; b < kBuckets; ++b) P->wide_warps[b] = wide_need[b];
     P->emit_bytes = align_up(e_floats * 4 + 16, 256);
     P->bp_bytes = align_up(bp_words * 4 + 16, 256);
 
@@ -276,7 +279,7 @@ static int viterbi_impl(const la_plan* P, void* d_ws, int32_t* d_first, int32_t*
         vp.chunk = la::viterbi_chunk_frames(P->row_max[b]);
         vp.first = d_first; vp.last_plus1 = d_last; vp.score = d_score; vp.status = d_status;
         vp.dp_dump = d_dp;
-        LA_CUDA(la::launch_viterbi(vp, b, P->wide_warps[b], static_cast<cudaStream_t>(stream)));
+        LA_CUDA(la::launch_viterbi(vp, kShape[b].K, kShape[b].warps, kShape[b].wide, static_cast<cudaStream_t>(stream)));
     }
     return LA_OK;
 }

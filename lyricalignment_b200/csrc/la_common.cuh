@@ -100,7 +100,7 @@ struct VitParams {
 };
 
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
-cudaError_t launch_viterbi(const VitParams& p, int bucket, int wide_warps, cudaStream_t stream);
+cudaError_t launch_viterbi(const VitParams& p, int K, int warps, bool wide, cudaStream_t stream);
 int viterbi_chunk_frames(int row_floats_max);
 int set_error(int code, const char* msg);   // records la_last_error(), returns code
 

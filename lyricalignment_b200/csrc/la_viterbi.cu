@@ -266,20 +266,22 @@ static cudaError_t launch_one(const VitParams& p, int threads, int grid, size_t 
     return cudaGetLastError();
 }
 
-// bucket: 0 -> K=1 warp, 1 -> K=2 warp, 2 -> K=4 warp, 3 -> K=4 wide, 4 -> K=8 wide
-cudaError_t launch_viterbi(const VitParams& p, int bucket, int wide_warps, cudaStream_t stream) {
+// K pairs per lane; wide: one CTA of `warps` warps per utterance, else 4 utterances (warps) per CTA
+cudaError_t launch_viterbi(const VitParams& p, int K, int warps, bool wide, cudaStream_t stream) {
     if (p.n_order <= 0) return cudaSuccess;
     constexpr int kWarpsPerCta = 4;
-    if (bucket <= 2) {
+    if (!wide) {
         const int grid = (p.n_order + kWarpsPerCta - 1) / kWarpsPerCta;
         const size_t smem = viterbi_smem_bytes(p.row_floats_max, p.chunk, kWarpsPerCta, kWarpsPerCta, false);
-        if (bucket == 0) return launch_one<1, false>(p, 32 * kWarpsPerCta, grid, smem, stream);
-        if (bucket == 1) return launch_one<2, false>(p, 32 * kWarpsPerCta, grid, smem, stream);
-        return launch_one<4, false>(p, 32 * kWarpsPerCta, grid, smem, stream);
+        return launch_one<1, false>(p, 32 * kWarpsPerCta, grid, smem, stream);
     }
-    const size_t smem = viterbi_smem_bytes(p.row_floats_max, p.chunk, 1, wide_warps, true);
-    if (bucket == 3) return launch_one<4, true>(p, 32 * wide_warps, p.n_order, smem, stream);
-    return launch_one<8, true>(p, 32 * wide_warps, p.n_order, smem, stream);
+    const size_t smem = viterbi_smem_bytes(p.row_floats_max, p.chunk, 1, warps, true);
+    switch (K) {
+        case 1: return launch_one<1, true>(p, 32 * warps, p.n_order, smem, stream);
+        case 2: return launch_one<2, true>(p, 32 * warps, p.n_order, smem, stream);
+        case 4: return launch_one<4, true>(p, 32 * warps, p.n_order, smem, stream);
+        default: return launch_one<8, true>(p, 32 * warps, p.n_order, smem, stream);
+    }
 }
 
 }  // namespace la

@@ -269,3 +269,23 @@ def test_quantised_ties_bit_exact():
         la.run_viterbi_core(dp, bt, e, b, lab)
         o = oracle.align_one(e, b, lab, want_tables=True)
         assert np.array_equal(bt[1:], o["bt"][1:]) and np.array_equal(dp, o["dp"])
+
+
+@pytest.mark.parametrize("L", [1023, 1024, 2047, 2500, 4096, 8191])
+def test_many_pairs_per_lane_buckets(L):
+    """L > 1023 uses 2 / 4 / 8 pairs per lane on a 32-warp CTA; checked cell-for-cell on step codes."""
+    rng = np.random.default_rng(L)
+    V = 40
+    lab = (np.arange(L) % 30 + 2 + rng.integers(0, 3, size=L) * 0).astype(np.int64)   # no adjacent repeats
+    T = L + 40
+    pred = (1.5 * rng.standard_normal((T, V))).astype(np.float32)
+    res, emis, codes = run_plan(pred, [lab], MODE_CTC, [T])
+    check_against_oracle(pred, [lab], MODE_CTC, [T], res, emis, codes, f"L{L}")
+    assert int(res.status[0]) == 0
+
+
+def test_label_row_longer_than_limit_is_refused():
+    from lyricalignment_b200._lib import LyricAlignError
+    with pytest.raises(LyricAlignError):
+        A.AlignPlan(MODE_CTC, 40, np.array([9000], np.int32), np.array([8192], np.int32),
+                    np.full(8192, 3, np.int32), 0)
