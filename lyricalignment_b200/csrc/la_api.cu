@@ -31,15 +31,15 @@ int set_error(int code, const char* msg) { return fail(code, msg); }
 
 // K3 launch shapes: one pair (blank + label state) per lane wherever possible -- the frame step is a
 // dependent chain whose length grows with the pairs a lane owns, so lanes are spent before pairs
-// per lane. Bucket 0: warp per utterance; 1..5: CTA per utterance with 2..32 warps; 6..8: 32 warps
-// with 2/4/8 pairs per lane (L up to 8191).
-constexpr int kBuckets = 9;
-struct BucketShape { int K; int warps; bool wide; };
-static const BucketShape kShape[kBuckets] = {{1, 1, false}, {1, 2, true}, {1, 4, true}, {1, 8, true}, {1, 16, true},
-                                             {1, 32, true}, {2, 32, true}, {4, 32, true}, {8, 32, true}};
+// per lane. One CTA per utterance using exactly ceil(pairs / 32K) warps (the launch is sized for the
+// widest utterance of its bucket, surplus warps exit). Buckets 0..2: K = 1 with up to 2 / 8 / 32
+// warps (so a batch of ordinary clips is ONE launch); 3..5: 32 warps with 2 / 4 / 8 pairs per lane.
+constexpr int kBuckets = 6;
+struct BucketShape { int K; int max_warps; };
+static const BucketShape kShape[kBuckets] = {{1, 2}, {1, 8}, {1, 32}, {2, 32}, {4, 32}, {8, 32}};
 static int bucket_for_pairs(int pairs) {
     for (int b = 0; b < kBuckets; ++b)
-        if (pairs <= 32 * kShape[b].K * kShape[b].warps) return b;
+        if (pairs <= 32 * kShape[b].K * kShape[b].max_warps) return b;
     return kBuckets - 1;
 }
 
@@ -51,6 +51,7 @@ struct la_plan {
     size_t emit_bytes = 0, bp_bytes = 0;
     std::vector<int32_t> order[kBuckets];
     int row_max[kBuckets] = {0};
+    int warps_max[kBuckets] = {0};
     // device metadata blob
     void* d_meta = nullptr;
     bool meta_pooled = false;
@@ -173,7 +174,9 @@ int la_plan_create(la_plan** out, int mode, int n_utt, int V, const int32_t* h_t
     size_t e_floats = 0, bp_words = 0;
     for (int u = 0; u < n_utt; ++u) {
         const BucketShape& sh = kShape[bucket_of[u]];
-        P->bp_pairs[u] = 32 * sh.warps * sh.K;
+        const int warps = std::max(1, (h_l_len[u] + 1 + 32 * sh.K - 1) / (32 * sh.K));
+        P->warps_max[bucket_of[u]] = std::max(P->warps_max[bucket_of[u]], warps);
+        P->bp_pairs[u] = 32 * warps * sh.K;
         P->e_off[u] = (int64_t)e_floats;
         e_floats += (size_t)h_t_len[u] * P->e_row[u];
         P->bp_off[u] = (int64_t)bp_words;
@@ -279,7 +282,7 @@ static int viterbi_impl(const la_plan* P, void* d_ws, int32_t* d_first, int32_t*
         vp.chunk = la::viterbi_chunk_frames(P->row_max[b]);
         vp.first = d_first; vp.last_plus1 = d_last; vp.score = d_score; vp.status = d_status;
         vp.dp_dump = d_dp;
-        LA_CUDA(la::launch_viterbi(vp, kShape[b].K, kShape[b].warps, kShape[b].wide, static_cast<cudaStream_t>(stream)));
+        LA_CUDA(la::launch_viterbi(vp, kShape[b].K, P->warps_max[b], true, static_cast<cudaStream_t>(stream)));
     }
     return LA_OK;
 }

@@ -41,7 +41,7 @@ template <int K, bool WIDE, bool DUMP>
 __global__ void __launch_bounds__(WIDE ? 1024 : 128) viterbi_kernel(const VitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarps = blockDim.x >> 5;
+    int nwarps = blockDim.x >> 5;                        // WIDE: narrowed to this utterance's own need below
     const int group = WIDE ? 0 : warp;                    // smem slice owner
     const int gthreads = WIDE ? blockDim.x : 32;
     const int gtid = WIDE ? tid : lane;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 128) viterbi_kernel(const VitPar
     float* stage0 = reinterpret_cast<float*>(gbase);
     uint64_t* full = reinterpret_cast<uint64_t*>(gbase + 2 * stage_bytes);
     double* fin = reinterpret_cast<double*>(gbase + 2 * stage_bytes + 16);
-    double* xchg = reinterpret_cast<double*>(smem + (size_t)(WIDE ? 1 : nwarps) * group_bytes);  // [2][nwarps]
+    double* xchg = reinterpret_cast<double*>(smem + (size_t)(WIDE ? 1 : nwarps) * group_bytes);  // [2][32]
 
     const bool active = slot < p.n_order;
     if (!WIDE && !active) return;                         // whole warp exits together
@@ -74,6 +74,12 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 128) viterbi_kernel(const VitPar
     const float* E = p.E + p.m.e_off[utt];
     const int pairs_pad = p.m.bp_pairs[utt];
     uint32_t* bp = p.bp + p.m.bp_off[utt];
+    if (WIDE) {
+        // the launch is sized for the widest utterance of the bucket; warps this one does not need
+        // leave before the first barrier (exited warps do not take part in __syncthreads)
+        nwarps = pairs_pad / (32 * K);
+        if (warp >= nwarps) return;
+    }
 
     if (gtid == 0) {
         mbar_init(&full[0], 1);
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 128) viterbi_kernel(const VitPar
             double ql = shfl_up_f64(pl[K - 1], 1);
             if (lane == 0) {
                 ql = -INFINITY;                            // pair 0: no left neighbour
-                if (WIDE && warp > 0) ql = xchg[((t - 1) & 1) * nwarps + warp - 1];
+                if (WIDE && warp > 0) ql = xchg[((t - 1) & 1) * 32 + warp - 1];
             }
             const int sh = (t & 7) * 4;
 #pragma unroll
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 128) viterbi_kernel(const VitPar
                 acc[j] |= nib << sh;
             }
             if (WIDE) {
-                if (lane == 31) xchg[(t & 1) * nwarps + warp] = pl[K - 1];
+                if (lane == 31) xchg[(t & 1) * 32 + warp] = pl[K - 1];
                 __syncthreads();
             }
             if (DUMP) {
@@ -248,7 +254,7 @@ int viterbi_chunk_frames(int row_floats_max) {
 
 size_t viterbi_smem_bytes(int row_floats_max, int chunk, int groups, int nwarps, bool wide) {
     const size_t group_bytes = 2 * (size_t)chunk * row_floats_max * 4 + 32;
-    return group_bytes * groups + (wide ? 2 * nwarps * sizeof(double) : 0);
+    return group_bytes * groups + (wide ? 2 * 32 * sizeof(double) : 0);
 }
 
 template <int K, bool WIDE>
