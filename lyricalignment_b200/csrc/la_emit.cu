@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(kEmitThreads, 2) emit_kernel(const EmitParams 
         const RowGeom g = row_geom(row, p.ld, V);
         const float* rowp = p.logits + row * p.ld;
 
-        float m = -INFINITY, s = 0.f;
+        float m = -INFINITY;
+        float2 s2 = make_float2(0.f, 0.f);                  // two interleaved partial sums (packed fp32x2 math)
         for (int c = 0; c < g.nchunks; ++c, ++it) {
             const int stage = it % kEmitStages;
             const uint32_t ph = (it / kEmitStages) & 1;
@@ -171,19 +172,21 @@ __global__ void __launch_bounds__(kEmitThreads, 2) emit_kernel(const EmitParams 
             }
             if (mx > -INFINITY) {
                 const float mn = fmaxf(m, mx);
-                const float mn2 = mn * kLog2e;
-                float acc = s * ex2_approx((m - mn) * kLog2e);
+                const float sc = ex2_approx((m - mn) * kLog2e);
+                const float2 l2 = make_float2(kLog2e, kLog2e), nm = make_float2(-mn * kLog2e, -mn * kLog2e);
+                float2 acc = make_float2(s2.x * sc, s2.y * sc);
 #pragma unroll
-                for (int k = 0; k < kF4PerThread; ++k) {      // 1 FFMA + 1 MUFU + 1 FADD per logit
-                    acc += ex2_approx(fmaf(v[k].x, kLog2e, -mn2));
-                    acc += ex2_approx(fmaf(v[k].y, kLog2e, -mn2));
-                    acc += ex2_approx(fmaf(v[k].z, kLog2e, -mn2));
-                    acc += ex2_approx(fmaf(v[k].w, kLog2e, -mn2));
+                for (int k = 0; k < kF4PerThread; ++k) {      // per 2 logits: 1 FFMA2 + 2 MUFU.EX2 + 1 FADD2
+                    const float2 a = __ffma2_rn(make_float2(v[k].x, v[k].y), l2, nm);
+                    const float2 b = __ffma2_rn(make_float2(v[k].z, v[k].w), l2, nm);
+                    acc = __fadd2_rn(acc, make_float2(ex2_approx(a.x), ex2_approx(a.y)));
+                    acc = __fadd2_rn(acc, make_float2(ex2_approx(b.x), ex2_approx(b.y)));
                 }
-                s = acc;
+                s2 = acc;
                 m = mn;
             }
         }
+        float s = s2.x + s2.y;
         if (tid < g.ntail) {                                // <= 3 floats past the aligned interior
             const int col = (int)((g.tail_start - row * p.ld * 4) >> 2) + tid;
             if (col >= lo && col <= hi) {
