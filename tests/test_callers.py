@@ -74,3 +74,21 @@ def test_runner_repoints_names_before_the_script_runs(tmp_path, monkeypatch, cap
     assert "ARGS ['-f', 'x.json', '--use-ctc-loss']" in out
     assert out.count("lyricalignment_b200.alignment") == 3
     assert "MAE 0.01500000000000001" in out
+
+
+def test_io_schema_roundtrip(tmp_path):
+    from lyricalignment_b200 import io as lio
+    src = [{"song_path": "/a/1.wav", "lyric": "你好吗", "on_offset": [[0.0, 0.5], [0.5, 1.0], [1.0, 1.5]]},
+           {"song_path": "/a/2.wav", "lyric": "好"}]
+    p = tmp_path / "d.json"
+    p.write_text(json.dumps(src, ensure_ascii=False))
+    recs = lio.read_data(str(p))
+    assert recs[0].text == "你好吗" and recs[0].lyric_onset_offset == src[0]["on_offset"] and recs[1].lyric_onset_offset is None
+    pred = [[[0.02, 0.48], [0.48, 1.0], [1.0, 1.52]], [[0.1, 0.12]]]
+    assert lio.format_prediction(pred[0], recs[0].text) == str([[0.02, 0.48, "你"], [0.48, 1.0, "好"], [1.0, 1.52, "吗"]])
+    out = tmp_path / "o.json"
+    lio.write_alignments(str(out), recs, pred, mae=[0.013, None])
+    back = lio.read_data(str(out))
+    assert back[0].lyric_onset_offset == pred[0] and back[1].text == "好"
+    with pytest.raises(AssertionError):
+        lio.read_data(str(tmp_path / "missing.json"))
