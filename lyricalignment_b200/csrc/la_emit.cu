@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kEmitThreads, 2) emit_kernel(const EmitParams 
     if (warp == kEmitConsumers / 32) {
         // ===================== producer warp: one elected lane drives the TMA ring ==========
         if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();   // every logit is read exactly once
             uint32_t it = 0;
             for (int64_t row = r0; row < r1; ++row) {
                 const RowGeom g = row_geom(row, p.ld, V);
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kEmitThreads, 2) emit_kernel(const EmitParams 
                     const int sz = min(g.cb, g.nbytes - off);
                     mbar_wait(&empty[stage], ph ^ 1);
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)sz);
-                    bulk_g2s(ring + stage * kEmitStageBytes, gbase + g.a_start + off, (uint32_t)sz, &full[stage]);
+                    bulk_g2s_hint(ring + stage * kEmitStageBytes, gbase + g.a_start + off, (uint32_t)sz, &full[stage], pol);
                 }
             }
         }

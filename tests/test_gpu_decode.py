@@ -289,3 +289,26 @@ def test_label_row_longer_than_limit_is_refused():
     with pytest.raises(LyricAlignError):
         A.AlignPlan(MODE_CTC, 40, np.array([9000], np.int32), np.array([8192], np.int32),
                     np.full(8192, 3, np.int32), 0)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_fuzz_ragged_plans_bit_exact(seed):
+    """Random ragged plans (T from 1, L from 0, repeats, infeasible rows mixed in): step codes, indices,
+    scores and statuses equal the C oracle run on the kernel's own emissions."""
+    rng = np.random.default_rng(1000 + seed)
+    mode = MODE_CTC if seed % 2 == 0 else MODE_CE
+    V = int(rng.integers(8, 300))
+    n = int(rng.integers(1, 40))
+    rows, t_len = [], []
+    for _ in range(n):
+        L = int(rng.integers(0, min(90, V - 2)))
+        T = int(rng.integers(1, 160))
+        if rng.random() < 0.15 and L > 2:
+            T = int(rng.integers(1, L))                   # infeasible on purpose
+        rows.append(_rand_rows(rng, 1, L, L, V - 2, p_rep=0.3)[0] if L else np.zeros(0, np.int64))
+        t_len.append(T)
+    quant = rng.random() < 0.5
+    pred = rng.standard_normal((sum(t_len), V))
+    pred = (np.round(pred * 2) / 2 if quant else 2.0 * pred).astype(np.float32)
+    res, emis, codes = run_plan(pred, rows, mode, t_len)
+    check_against_oracle(pred, rows, mode, t_len, res, emis, codes, f"fuzz{seed}")
