@@ -1,6 +1,7 @@
 // la_api.cu -- the C ABI (include/lyricalign.h): plans, workspace layout, kernel dispatch.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -413,6 +414,7 @@ static int emit_rows(const la_plan* P, const float* d_logits, int64_t ld, const 
     ep.logits = d_logits; ep.ld = ld; ep.sil = d_sil; ep.ld_sil = ld_sil;
     ep.E = static_cast<float*>(d_ws);
     ep.row0 = row0;
+    { static const int hint = [] { const char* e = getenv("LA_EMIT_L2_HINT"); return e ? atoi(e) : 0; }(); ep.l2_hint = hint; }
     ep.n_rows = (int)n_rows;
     LA_CUDA(la::launch_emit(ep, P->sm_count, stream));
     return LA_OK;

@@ -96,6 +96,7 @@ struct EmitParams {
     float* E;              // workspace emission area
     int64_t row0;          // batch row index of logits row 0 (host path streams row ranges)
     int n_rows;
+    int l2_hint;           // 1: L2 evict-first policy on the logits bulk copies (A/B knob LA_EMIT_L2_HINT)
 };
 
 struct VitParams {

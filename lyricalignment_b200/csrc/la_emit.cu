@@ -6,8 +6,8 @@
 // emission rows the DP needs (blank + L label columns per frame).
 //
 // Shape of the kernel (HBM-bound, 84.5 KB per frame at V = 21129):
-//   * persistent CTAs, 2 per SM, each owning a contiguous range of frame rows;
-//   * one producer warp streams every row through a 6-stage x 16 KB shared-memory ring with
+//   * persistent CTAs, 3 per SM, each owning a contiguous range of frame rows;
+//   * one producer warp streams every row through a 4-stage x 16 KB shared-memory ring with
 //     1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); rows are only 4-byte aligned
 //     (V is odd), so the copy covers the 16-byte-aligned interior and <= 3 tail floats are read
 //     directly;
@@ -18,6 +18,8 @@
 //     logits (L2-hot, the row has just streamed through) and apply the reference's exact
 //     formulas in fp32: (z - max) - log(sum); naive 1/(1+exp(-z)) sigmoid; log(1 - s); add;
 //     clip at -1000 AFTER the add.
+#include <cstdlib>
+
 #include "la_common.cuh"
 
 namespace la {
@@ -25,7 +27,6 @@ namespace la {
 constexpr int kEmitConsumers = 256;
 constexpr int kEmitThreads = kEmitConsumers + 32;
 constexpr int kEmitStageBytes = 16384;
-constexpr int kEmitStages = 6;
 constexpr int kF4PerThread = kEmitStageBytes / 16 / kEmitConsumers;   // 4
 
 struct RowGeom {
@@ -64,8 +65,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 constexpr float kLog2e = 1.4426950408889634f;
 
-template <int MODE>
-__global__ void __launch_bounds__(kEmitThreads, 2) emit_kernel(const EmitParams p) {
+// STAGES x 16 KB ring per CTA, CTAS resident CTAs per SM (6 x 2 and 4 x 3 both keep 192 KB in flight per SM)
+template <int MODE, int kEmitStages, int CTAS>
+__global__ void __launch_bounds__(kEmitThreads, CTAS) emit_kernel(const EmitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kEmitStages * kEmitStageBytes);
@@ -102,7 +104,8 @@ __global__ void __launch_bounds__(kEmitThreads, 2) emit_kernel(const EmitParams 
                     const int sz = min(g.cb, g.nbytes - off);
                     mbar_wait(&empty[stage], ph ^ 1);
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)sz);
-                    bulk_g2s_hint(ring + stage * kEmitStageBytes, gbase + g.a_start + off, (uint32_t)sz, &full[stage], pol);
+                    if (p.l2_hint) bulk_g2s_hint(ring + stage * kEmitStageBytes, gbase + g.a_start + off, (uint32_t)sz, &full[stage], pol);
+                    else bulk_g2s(ring + stage * kEmitStageBytes, gbase + g.a_start + off, (uint32_t)sz, &full[stage]);
                 }
             }
         }
@@ -267,9 +270,19 @@ __global__ void gather_logp_kernel(const EmitParams p) {
     if (threadIdx.x == 0) Erow[0] = p.sil[row * p.ld_sil];
 }
 
-size_t emit_smem_bytes() {
-    return (size_t)kEmitStages * kEmitStageBytes + 2 * kEmitStages * sizeof(uint64_t) +
-           2 * (kEmitConsumers / 32) * sizeof(float2);
+size_t emit_smem_bytes(int stages) {
+    return (size_t)stages * kEmitStageBytes + 2 * stages * sizeof(uint64_t) + 2 * (kEmitConsumers / 32) * sizeof(float2);
+}
+
+template <int MODE, int STAGES, int CTAS>
+static cudaError_t launch_emit_variant(const EmitParams& p, int sm_count, cudaStream_t stream) {
+    const size_t smem = emit_smem_bytes(STAGES);
+    cudaError_t e = cudaFuncSetAttribute(emit_kernel<MODE, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int grid = CTAS * sm_count;
+    if (grid > p.n_rows) grid = p.n_rows;
+    emit_kernel<MODE, STAGES, CTAS><<<grid, kEmitThreads, smem, stream>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream) {
@@ -278,18 +291,14 @@ cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream) 
         gather_logp_kernel<<<p.n_rows, 128, 0, stream>>>(p);
         return cudaGetLastError();
     }
-    const size_t smem = emit_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(emit_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(emit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int grid = 2 * sm_count;
-    if (grid > p.n_rows) grid = p.n_rows;
-    if (p.m.mode == 0)
-        emit_kernel<0><<<grid, kEmitThreads, smem, stream>>>(p);
-    else
-        emit_kernel<1><<<grid, kEmitThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+    // Default: 3 CTAs/SM with 4-stage rings. Measured A/B on one box (profiles/k2_tuning_r1.md): with the
+    // SM clock power-capped to ~1.7 GHz (the tensor-heavy K1 runs right before), 2 CTAs x 6 stages fell to
+    // 0.90 of the HBM peak (consumer latency-bound), 3 CTAs x 4 stages holds 0.98. LA_EMIT_VARIANT=0 selects
+    // the old shape for comparison.
+    static const int variant = [] { const char* e = getenv("LA_EMIT_VARIANT"); return e ? atoi(e) : 1; }();
+    if (variant == 0)
+        return p.m.mode == 0 ? launch_emit_variant<0, 6, 2>(p, sm_count, stream) : launch_emit_variant<1, 6, 2>(p, sm_count, stream);
+    return p.m.mode == 0 ? launch_emit_variant<0, 4, 3>(p, sm_count, stream) : launch_emit_variant<1, 4, 3>(p, sm_count, stream);
 }
 
 }  // namespace la
