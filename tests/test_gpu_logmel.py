@@ -94,3 +94,31 @@ def test_writes_into_prezeroed_encoder_window():
     padded = LA.pad_or_trim(mel, LA.N_FRAMES)
     assert padded.shape == (80, 3000) and torch.all(padded[:, 700:] == 0)
     assert LA.decode_frames(mel.shape[-1]) == 350 and LA.decode_frames(501) == 250 and LA.decode_frames(503) == 252
+
+
+def test_five_minute_song_and_chunked_framing():
+    """BASELINE config 3 front end: 300 s = 30 000 mel frames = 10 encoder chunks (align_model.py:93-104);
+    the max-8 floor is global over the whole song."""
+    rng = np.random.default_rng(5)
+    a = _signal(rng, 16000 * 300, "survey")
+    got = LA.log_mel_spectrogram(a).cpu().numpy()
+    assert got.shape == (80, 30000)
+    _close(got, oracle.log_mel_spectrogram(a))
+    assert sum(LA.decode_frames(min(3000, 30000 - s)) for s in range(0, 30000, 3000)) == 15000
+
+
+def test_unaligned_clip_offsets_take_the_plain_load_path():
+    """Clip starts that are not multiples of 4 samples cannot use TMA; results must not change."""
+    rng = np.random.default_rng(6)
+    clips = [_signal(rng, n, "noise") for n in (20001, 33333, 16000)]
+    offs, pos = [], 3
+    for c in clips:
+        offs.append(pos)
+        pos += len(c) + 1          # odd gaps -> every alignment class
+    wave = np.zeros(pos + 8, np.float32)
+    for o, c in zip(offs, clips):
+        wave[o:o + len(c)] = c
+    out, ooff, frames = LA.log_mel_spectrogram_ragged(torch.from_numpy(wave).cuda(), offs, [len(c) for c in clips])
+    out = out.cpu().numpy()
+    for c, o, f in zip(clips, ooff, frames):
+        _close(out[o:o + 80 * f].reshape(80, f), oracle.log_mel_spectrogram(c))
