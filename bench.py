@@ -165,6 +165,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    import faulthandler
+    faulthandler.dump_traceback_later(420, exit=True)     # a hung collective must not eat the whole time budget
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -177,6 +179,7 @@ def main():
         run_reference_arm(args, synth)
         return
 
+    t_begin = time.perf_counter()
     import torch.distributed as dist
     from lyricalignment_b200 import _lib, alignment as A, audio as LA, sharded
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -225,12 +228,28 @@ def main():
             res = A.AlignResult(first, last, score, status, l_len)
             gather_device(res, dev, dist)
 
-    def gather_device(res, dev, dist):
-        # NCCL gather of the alignments to rank 0 (payload stays on the device until rank 0 reads it)
-        payload = torch.cat([res.first, res.last_plus1, res.status, res.score.view(torch.int32)])
-        out = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
-        dist.gather(payload, out, dst=0)
+    # NCCL gather of the alignments to rank 0. Ranks own different clips, so their payloads differ in
+    # length: every rank sends a buffer padded to the common maximum (sizes exchanged once, at set-up).
+    n_payload = 2 * plan.total_labels + 3 * plan.n_utt
+    if world > 1:
+        mx = torch.tensor([n_payload], dtype=torch.int64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        n_payload_max = int(mx.item())
+        payload = torch.zeros(n_payload_max, dtype=torch.int32, device=dev)
+        gathered = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
 
+    def gather_device(res, dev, dist):
+        L, U = plan.total_labels, plan.n_utt
+        payload[0:L] = res.first
+        payload[L:2 * L] = res.last_plus1
+        payload[2 * L:2 * L + U] = res.status
+        payload[2 * L + U:2 * L + 3 * U] = res.score.view(torch.int32)
+        dist.gather(payload, gathered, dst=0)
+
+    def note(msg):
+        if rank == 0:
+            print(f"[bench +{time.perf_counter() - t_begin:6.1f}s] {msg}", file=sys.stderr, flush=True)
+    note("inputs ready, warm-up")
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -252,6 +271,7 @@ def main():
     if world > 1:
         dist.barrier()
     clk = clocks.stop() if rank == 0 else None
+    note("device-resident timing done")
     ms_total = t_start.elapsed_time(t_end)
     mel_ms = statistics.mean(m.elapsed_time(a) for m, a, b in ev)
     emit_ms = statistics.mean(a.elapsed_time(b) for m, a, b in ev)
@@ -332,8 +352,10 @@ def main():
                 tot += len(out[0])
             return tot
         pool_wave_end = int(w_off[pool_n - 1] + n_samp[pool_n - 1])
+        note("e2e warm-up")
         e2e_step()
         dropin_step()
+        note("e2e timing")
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -368,6 +390,8 @@ def main():
                    "sample": f"first {n_cpu} clips of the workload ({sum(batch.durations[:n_cpu]):.0f} audio-s), "
                              f"median of 3 passes, {secs:.2f} s per pass, host cpu_count={os.cpu_count()}"}
 
+    note("done")
+    faulthandler.cancel_dump_traceback_later()
     if rank == 0:
         line = {
             "metric": "aligned audio-sec/sec (alignment decode path)", "value": round(value, 1), "unit": "audio-s/s",
