@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 128) viterbi_kernel(const VitPar
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int nwarps = blockDim.x >> 5;                        // WIDE: narrowed to this utterance's own need below
     const int group = WIDE ? 0 : warp;                    // smem slice owner
-    const int gthreads = WIDE ? blockDim.x : 32;
     const int gtid = WIDE ? tid : lane;
     const int slot = WIDE ? blockIdx.x : blockIdx.x * nwarps + warp;
 
