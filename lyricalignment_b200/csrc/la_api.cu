@@ -72,13 +72,10 @@ struct HostCtx {
     size_t out_bytes = 0;
     void* h_out = nullptr;      // pinned bounce buffer for the results
     size_t h_out_bytes = 0;
-    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_vit = nullptr;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_reset = nullptr;
-    int* d_progress = nullptr;  // rows of the batch whose emissions are complete (streamed K3)
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
 static HostCtx g_host[64];
-
-__global__ void publish_progress_kernel(int* progress, int rows) { *progress = rows; }
 
 // Plan metadata lives in pooled 64 KiB device blocks: cudaMalloc / cudaFree (the latter a device-wide
 // sync) cost milliseconds next to a 40 MB clip, and the reference's entry points decode one clip
@@ -270,7 +267,7 @@ int la_emit(const la_plan* P, const float* d_logits, int64_t ld, const float* d_
 }
 
 static int viterbi_impl(const la_plan* P, void* d_ws, int32_t* d_first, int32_t* d_last, double* d_score,
-                        int32_t* d_status, double* d_dp, void* stream, const int* d_progress = nullptr) {
+                        int32_t* d_status, double* d_dp, void* stream) {
     if (!P || !d_ws || !d_score || !d_status) return fail(LA_ERR_ARG, "null argument");
     if (P->total_L > 0 && (!d_first || !d_last)) return fail(LA_ERR_ARG, "null output");
     LA_CUDA(cudaSetDevice(P->device));
@@ -286,7 +283,6 @@ static int viterbi_impl(const la_plan* P, void* d_ws, int32_t* d_first, int32_t*
         vp.chunk = la::viterbi_chunk_frames(P->row_max[b]);
         vp.first = d_first; vp.last_plus1 = d_last; vp.score = d_score; vp.status = d_status;
         vp.dp_dump = d_dp;
-        vp.progress = d_progress;
         LA_CUDA(la::launch_viterbi(vp, kShape[b].K, P->warps_max[b], true, static_cast<cudaStream_t>(stream)));
     }
     return LA_OK;
@@ -338,9 +334,6 @@ int la_align_host(la_plan* P, const float* h_logits, int64_t ld, int32_t* h_firs
     if (!C.s_copy) {
         LA_CUDA(cudaStreamCreateWithFlags(&C.s_copy, cudaStreamNonBlocking));
         LA_CUDA(cudaStreamCreateWithFlags(&C.s_comp, cudaStreamNonBlocking));
-        LA_CUDA(cudaStreamCreateWithFlags(&C.s_vit, cudaStreamNonBlocking));
-        LA_CUDA(cudaEventCreateWithFlags(&C.ev_reset, cudaEventDisableTiming));
-        LA_CUDA(cudaMalloc(reinterpret_cast<void**>(&C.d_progress), 256));
         for (int i = 0; i < 2; ++i) {
             LA_CUDA(cudaEventCreateWithFlags(&C.ev_copied[i], cudaEventDisableTiming));
             LA_CUDA(cudaEventCreateWithFlags(&C.ev_done[i], cudaEventDisableTiming));
@@ -376,21 +369,6 @@ int la_align_host(la_plan* P, const float* h_logits, int64_t ld, int32_t* h_firs
     double* d_score = reinterpret_cast<double*>(o + 2 * lab_bytes);
     int32_t* d_status = reinterpret_cast<int32_t*>(o + 2 * lab_bytes + sc_bytes);
 
-    // Per-clip calls (the reference's batch size 1): K3 is a latency chain of ~0.16 us per frame, so it
-    // is launched FIRST on its own stream and consumes emission rows as K2 publishes them, hiding
-    // behind the H2D copy instead of running after it. Large batches keep the simple order (K3 is
-    // < 1 % there and its CTAs would only sit polling).
-    static const bool allow_stream = [] { const char* e = getenv("LA_HOST_STREAM_K3"); return e ? atoi(e) != 0 : true; }();
-    const bool streamed = allow_stream && P->n_utt <= 8 && P->total_T > 0;
-    cudaStream_t s_res = C.s_comp;
-    if (streamed) {
-        LA_CUDA(cudaMemsetAsync(C.d_progress, 0, sizeof(int), C.s_comp));
-        LA_CUDA(cudaEventRecord(C.ev_reset, C.s_comp));
-        LA_CUDA(cudaStreamWaitEvent(C.s_vit, C.ev_reset, 0));
-        rc = viterbi_impl(P, C.d_ws, d_first, d_last, d_score, d_status, nullptr, C.s_vit, C.d_progress);
-        if (rc) return rc;
-        s_res = C.s_vit;
-    }
     // chunked H2D (copy stream) overlapped with K2 (compute stream), two staging buffers
     int64_t row = 0;
     int i = 0;
@@ -405,20 +383,16 @@ int la_align_host(la_plan* P, const float* h_logits, int64_t ld, int32_t* h_firs
         LA_CUDA(cudaStreamWaitEvent(C.s_comp, C.ev_copied[sbuf], 0));
         rc = emit_rows(P, static_cast<const float*>(C.d_stage[sbuf]), ld, nullptr, 0, C.d_ws, row, n, C.s_comp);
         if (rc) return rc;
-        if (streamed) publish_progress_kernel<<<1, 1, 0, C.s_comp>>>(C.d_progress, (int)(row + n));
         LA_CUDA(cudaEventRecord(C.ev_done[sbuf], C.s_comp));
         used[sbuf] = true;
         row += n;
         ++i;
     }
-    if (!streamed) {
-        rc = la_viterbi(P, C.d_ws, d_first, d_last, d_score, d_status, C.s_comp);
-        if (rc) return rc;
-    }
+    rc = la_viterbi(P, C.d_ws, d_first, d_last, d_score, d_status, C.s_comp);
+    if (rc) return rc;
     // one D2H of the packed results into the pinned bounce buffer, then scatter on the host
-    LA_CUDA(cudaMemcpyAsync(C.h_out, C.d_out, out_bytes - 64, cudaMemcpyDeviceToHost, s_res));
-    LA_CUDA(cudaStreamSynchronize(s_res));
-    if (streamed) LA_CUDA(cudaStreamSynchronize(C.s_comp));   // staging buffers are reused by the next call
+    LA_CUDA(cudaMemcpyAsync(C.h_out, C.d_out, out_bytes - 64, cudaMemcpyDeviceToHost, C.s_comp));
+    LA_CUDA(cudaStreamSynchronize(C.s_comp));
     const unsigned char* h = static_cast<const unsigned char*>(C.h_out);
     if (P->total_L > 0) {
         memcpy(h_first, h, (size_t)P->total_L * 4);

@@ -112,8 +112,6 @@ struct VitParams {
     double* score;
     int32_t* status;
     double* dp_dump;        // debug/parity only: full fp64 table [T][2L+1] of a 1-utterance plan, or null
-    const int* progress;    // host path only: batch rows whose emissions are complete (published in
-                            // stream order after every K2 chunk); K3 consumes frames as they appear. Null = all ready
 };
 
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);

@@ -88,16 +88,9 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 128) viterbi_kernel(const VitPar
     if (WIDE) __syncthreads(); else __syncwarp();
 
     const int nchunks = (T + kVitChunk - 1) / kVitChunk;
-    const int row_base = p.m.t_off[utt];
     auto issue = [&](int c) {
         const int rows = min(kVitChunk, T - c * kVitChunk);
         const uint32_t bytes = (uint32_t)rows * wrow * 4;
-        if (p.progress) {
-            // streamed host path: wait until K2 has published these frames' emission rows
-            const int need = row_base + c * kVitChunk + rows;
-            while (*reinterpret_cast<const volatile int*>(p.progress) < need) __nanosleep(200);
-            __threadfence();
-        }
         fence_proxy_async();
         mbar_arrive_expect_tx(&full[c & 1], bytes);
         bulk_g2s(reinterpret_cast<unsigned char*>(stage0) + (c & 1) * stage_bytes,
