@@ -241,18 +241,18 @@ def onoff_seconds(res: AlignResult, hop_size_second: float = 0.02):
 
 
 def _to_onoff(res: AlignResult, hop_size_second: float) -> List[List[List[float]]]:
-    out, p = [], 0
-    for u, n in enumerate(res.l_len):
-        n = int(n)
-        st = int(res.status[u])
-        if st == _lib.UTT_EMPTY:       # reference: cur_label[0] on an empty array (:152)
+    status = res.status
+    if status.size and status.max() != 0:
+        u = int(np.nonzero(status)[0][0])          # first failing utterance in batch order decides
+        if int(status[u]) == _lib.UTT_EMPTY:        # reference: cur_label[0] on an empty array (:152)
             raise IndexError("index 0 is out of bounds for axis 0 with size 0")
-        if st == _lib.UTT_INFEASIBLE:  # reference: correct_path.index(k * 2 + 1) (:183)
-            raise ValueError("label state is not in list")
-        f = res.first[p:p + n].tolist()
-        l = res.last_plus1[p:p + n].tolist()
-        # utils/alignment.py:185: float(index) * hop in Python fp64
-        out.append([[float(a) * hop_size_second, float(b) * hop_size_second] for a, b in zip(f, l)])
+        raise ValueError("label state is not in list")   # reference: correct_path.index(k * 2 + 1) (:183)
+    # utils/alignment.py:185: float(index) * hop in Python fp64 == IEEE fp64 multiply, done in one numpy pass
+    hop = float(hop_size_second)
+    pairs = np.stack([res.first.astype(np.float64) * hop, res.last_plus1.astype(np.float64) * hop], axis=1).tolist()
+    out, p = [], 0
+    for n in res.l_len.tolist():
+        out.append(pairs[p:p + n])
         p += n
     return out
 
