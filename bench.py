@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--k1-sms", type=int, default=28,
+                    help="SMs given to K1 while it runs concurrently with K2/K3 on a second stream (0 = run K1, K2, K3 back to back)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -211,12 +213,36 @@ def main():
     mel_ws = torch.empty(int(lib.la_logmel_workspace_bytes(len(n_samp), int(n_samp.astype(np.int64).sum()))),
                          dtype=torch.uint8, device=dev)
 
+    # K1 works on the waveforms, K2/K3 on the head logits (the stock encoder sits between them), so inside
+    # one pass over the batch they are independent: K1 runs on a side stream on its own SM partition.
+    overlap = args.k1_sms > 0
+    sms_total = torch.cuda.get_device_properties(dev).multi_processor_count
+    if overlap:
+        lib.la_set_sm_budget(args.k1_sms, sms_total - args.k1_sms)
+        side = torch.cuda.Stream(device=dev)
+        ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+        ev_k1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + args.warmup)]
+    step_no = [0]
+
     def step(ev_m=None, ev_a=None, ev_b=None):
         if ev_m is not None:
             ev_m.record()
-        _lib.check(lib.la_logmel_ragged(wave.data_ptr(), len(n_samp), w_off.ctypes.data, n_samp.ctypes.data,
-                                        mel_out.data_ptr(), mel_off.ctypes.data, mel_frames.ctypes.data,
-                                        mel_ws.data_ptr(), stream), "la_logmel_ragged")
+        if overlap:
+            ev_fork.record()
+            side.wait_event(ev_fork)
+            with torch.cuda.stream(side):
+                k1a, k1b = ev_k1[step_no[0] % len(ev_k1)]
+                k1a.record()
+                _lib.check(lib.la_logmel_ragged(wave.data_ptr(), len(n_samp), w_off.ctypes.data, n_samp.ctypes.data,
+                                                mel_out.data_ptr(), mel_off.ctypes.data, mel_frames.ctypes.data,
+                                                mel_ws.data_ptr(), side.cuda_stream), "la_logmel_ragged")
+                k1b.record()
+                ev_join.record()
+            step_no[0] += 1
+        else:
+            _lib.check(lib.la_logmel_ragged(wave.data_ptr(), len(n_samp), w_off.ctypes.data, n_samp.ctypes.data,
+                                            mel_out.data_ptr(), mel_off.ctypes.data, mel_frames.ctypes.data,
+                                            mel_ws.data_ptr(), stream), "la_logmel_ragged")
         if ev_a is not None:
             ev_a.record()
         _lib.check(lib.la_emit(plan.handle, logits.data_ptr(), V, None, 0, ws.data_ptr(), stream), "la_emit")
@@ -227,6 +253,8 @@ def main():
         if world > 1:
             res = A.AlignResult(first, last, score, status, l_len)
             gather_device(res, dev, dist)
+        if overlap:
+            torch.cuda.current_stream(dev).wait_event(ev_join)
 
     # NCCL gather of the alignments to rank 0. Ranks own different clips, so their payloads differ in
     # length: every rank sends a buffer padded to the common maximum (sizes exchanged once, at set-up).
@@ -271,9 +299,13 @@ def main():
     if world > 1:
         dist.barrier()
     clk = clocks.stop() if rank == 0 else None
+    lib.la_set_sm_budget(0, 0)                      # the e2e legs below run K1 and K2 back to back on the whole chip
     note("device-resident timing done")
     ms_total = t_start.elapsed_time(t_end)
-    mel_ms = statistics.mean(m.elapsed_time(a) for m, a, b in ev)
+    if overlap:
+        mel_ms = statistics.mean(a.elapsed_time(b) for a, b in ev_k1[-args.steps:]) if args.steps <= len(ev_k1) else float("nan")
+    else:
+        mel_ms = statistics.mean(m.elapsed_time(a) for m, a, b in ev)
     emit_ms = statistics.mean(a.elapsed_time(b) for m, a, b in ev)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -305,11 +337,13 @@ def main():
     step_ms = ms_total / args.steps
     kernels = {"k1_logmel_ms": round(mel_ms, 4), "k1_tf32_tflops": round(mel_flops / (mel_ms / 1e3) / 1e12, 1),
                "k1_algorithmic_gbs": round(mel_bytes / (mel_ms / 1e3) / 1e9, 1),
-               "k2_emit_ms": round(emit_ms, 4), "k3_viterbi_and_rest_ms": round(step_ms - mel_ms - emit_ms, 4),
+               "k2_emit_ms": round(emit_ms, 4),
+               "k3_viterbi_and_rest_ms": round(step_ms - emit_ms - (0.0 if overlap else mel_ms), 4),
+               "k1_concurrent_with_k2": bool(overlap), "k1_sms": args.k1_sms if overlap else sms_total,
                # K3 is latency-bound (a frame step is a dependent chain): its nominal HBM figure, for the record
                "k3_algorithmic_gbs": round((2 * 4.0 * float(np.sum(batch.t_len.astype(np.int64) * (l_len + 1))) +
                                             8.0 * float(np.sum(batch.t_len.astype(np.int64) * ((l_len + 32) // 32 * 32) // 8)))
-                                           / max(step_ms - mel_ms - emit_ms, 1e-6) / 1e6, 1)}
+                                           / max(step_ms - emit_ms - (0.0 if overlap else mel_ms), 1e-6) / 1e6, 1)}
 
     # ---- e2e + cpu baseline on rank 0's pinned pool ----------------------------------------
     e2e, cpu = None, None
@@ -401,7 +435,9 @@ def main():
             "config": {"workload": f"configs[1]: Opencpop-test-shaped batch, {args.clips} clips of 5-15 s per GPU, "
                                    f"V=21129 CTC decode, {plan.total_labels} syllables, {total_T} frames",
                        "l2_policy": f"inputs larger than L2 ({4.0 * total_T * V / 1e9:.1f} GB of logits resident in HBM per GPU)",
-                       "parallelism": f"utterance-sharded x{world}" + (", NCCL gather of alignments in the step" if world > 1 else "")},
+                       "parallelism": f"utterance-sharded x{world}" + (", NCCL gather of alignments in the step" if world > 1 else ""),
+                       "streams": (f"K1 on a side stream on {args.k1_sms} SMs, concurrent with K2/K3 on the other {sms_total - args.k1_sms}"
+                                   if overlap else "K1, K2, K3 back to back on one stream")},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": (plan.num_launches + 3) * args.steps, "clocks": clk,
         }

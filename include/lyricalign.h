@@ -63,6 +63,12 @@ typedef enum la_utt_status {
 typedef struct la_plan la_plan;
 
 const char* la_version(void);
+/* Process-wide SM budgets, for running K1 and K2 CONCURRENTLY on two streams (they are persistent
+ * kernels sized to the whole chip by default, so one would otherwise queue behind the other):
+ * K1 launches at most `logmel_ctas` CTAs (one per SM, 0 = all SMs), K2 sizes its grid for
+ * `emit_sms` SMs (0 = all). Launch K1 first; its CTAs occupy whole SMs (220 KB of shared memory), K2's
+ * then fill the rest. */
+void la_set_sm_budget(int logmel_ctas, int emit_sms);
 const char* la_last_error(void);            /* thread-local, human readable */
 int la_device_count(void);
 

@@ -28,6 +28,8 @@ static int cuda_fail(cudaError_t e, const char* where) {
 
 namespace la {
 int set_error(int code, const char* msg) { return fail(code, msg); }
+int g_logmel_ctas = 0;
+int g_emit_sms = 0;
 }
 
 // K3 launch shapes: one pair (blank + label state) per lane wherever possible -- the frame step is a
@@ -127,6 +129,10 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 extern "C" {
 
 const char* la_version(void) { return "lyricalign-b200 0.1 (sm_100a)"; }
+void la_set_sm_budget(int logmel_ctas, int emit_sms) {
+    la::g_logmel_ctas = logmel_ctas > 0 ? logmel_ctas : 0;
+    la::g_emit_sms = emit_sms > 0 ? emit_sms : 0;
+}
 const char* la_last_error(void) { return g_err.c_str(); }
 int la_device_count(void) {
     int n = 0;
@@ -419,6 +425,6 @@ static int emit_rows(const la_plan* P, const float* d_logits, int64_t ld, const 
     ep.row0 = row0;
     { static const int hint = [] { const char* e = getenv("LA_EMIT_L2_HINT"); return e ? atoi(e) : 0; }(); ep.l2_hint = hint; }
     ep.n_rows = (int)n_rows;
-    LA_CUDA(la::launch_emit(ep, P->sm_count, stream));
+    LA_CUDA(la::launch_emit(ep, la::g_emit_sms > 0 ? std::min(la::g_emit_sms, P->sm_count) : P->sm_count, stream));
     return LA_OK;
 }

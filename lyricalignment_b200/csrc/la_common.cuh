@@ -117,7 +117,9 @@ struct VitParams {
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
 cudaError_t launch_viterbi(const VitParams& p, int K, int warps, bool wide, cudaStream_t stream);
 int viterbi_chunk_frames(int row_floats_max);
-int set_error(int code, const char* msg);   // records la_last_error(), returns code
+int set_error(int code, const char* msg);
+extern int g_logmel_ctas;   // la_set_sm_budget(): 0 = whole chip
+extern int g_emit_sms;   // records la_last_error(), returns code
 
 constexpr double kFloor = -10000000.0;   // utils/alignment.py:144
 constexpr float kClip = -1000.0f;        // utils/alignment.py:132,134 / :18,20

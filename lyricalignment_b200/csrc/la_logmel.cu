@@ -634,7 +634,8 @@ static int logmel_run(const float* d_wave, float* d_out, const std::vector<la::C
     const size_t smem = logmel_smem_bytes();
     e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "smem attr: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
-    logmel_kernel<<<std::min(n_tiles, sms), kLogmelThreads, smem, stream>>>(p);
+    const int ctas = la::g_logmel_ctas > 0 ? std::min(la::g_logmel_ctas, sms) : sms;
+    logmel_kernel<<<std::min(n_tiles, ctas), kLogmelThreads, smem, stream>>>(p);
     const int fx = std::max(1, std::min(64, (kMels * max_frames + 255) / 256));
     logmel_finalize_kernel<<<dim3(fx, (unsigned)clips.size()), 256, 0, stream>>>(p);
     e = cudaGetLastError();
