@@ -61,6 +61,10 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, 
         "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+// L2 prefetch of a global range (16-byte aligned, multiple of 16 bytes)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -258,6 +258,18 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 for (int g = rp.lo; g < rp.hi; ++g)
                     bulk_g2s(raw + g * kRawGroupPitch, src + g * kRawGroup * kHop,
                              min(kRawGroup, kRawRows - g * kRawGroup) * kHop * 4, raw_full);
+                // the staging buffer is single, so the next tile's waveform can only be COPIED once this
+                // tile is transformed -- but it can already be pulled into L2
+                const int nt = tile + gridDim.x;
+                if (nt < p.n_tiles) {
+                    const ClipDesc cn = p.clips[p.tile_clip[nt]];
+                    const int fn = (nt - cn.tile0) * kTileM;
+                    const int64_t jn = (int64_t)fn * kHop - kNfft / 2;
+                    const RawPlan rn = raw_plan(cn, jn, fn);
+                    if (rn.hi > rn.lo)
+                        bulk_prefetch_l2(p.wave + cn.wave_off + jn + (int64_t)rn.lo * kRawGroup * kHop,
+                                         (uint32_t)(min(rn.hi * kRawGroup, kRawRows) - rn.lo * kRawGroup) * kHop * 4);
+                }
                 trace(p.dbg, 3, tl, 1);
                 for (int ks = 0; ks < kKSteps; ++ks, ++it) {
                     const int s = it % kBStages;
