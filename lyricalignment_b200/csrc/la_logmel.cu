@@ -191,19 +191,21 @@ __device__ __forceinline__ float rna_tf32(float x) {      // round-to-nearest TF
 // groups [lo, hi) lie fully inside the clip and take one TMA bulk copy each, the others (clip
 // edges: reflect padding, ragged end) are filled by plain loads.
 struct RawPlan { int need, lo, hi; };
-__device__ __forceinline__ RawPlan raw_plan(const ClipDesc& c, int64_t j0, int f0) {
+// 32-bit arithmetic with constant divisors only (n_samples < 2^31): every thread of the transform warps
+// and the producer evaluate this once per tile, and the first version's 64-bit divisions cost 1.6 us there.
+__device__ __forceinline__ RawPlan raw_plan(const ClipDesc& c, int j0, int f0) {
+    constexpr int G = kRawGroup * kHop;                                  // 1280 samples per group
     RawPlan r;
     const int last_valid = min(kTileM, c.n_frames - f0) - 1;            // last frame row of the tile that is stored
-    const int64_t need_hi = (int64_t)last_valid * kHop + kNfft;         // tile-relative, exclusive
-    r.need = min(kRawGroups, (int)((need_hi + kRawGroup * kHop - 1) / (kRawGroup * kHop)));
+    const int need_hi = last_valid * kHop + kNfft;                      // tile-relative, exclusive
+    r.need = min(kRawGroups, (need_hi + G - 1) / G);
     r.lo = j0 < 0 ? 1 : 0;
-    const int64_t inside = ((int64_t)c.n_samples - j0) / (kRawGroup * kHop);   // groups ending at or before the clip end
-    r.hi = (int)max((int64_t)r.lo, min((int64_t)r.need, inside));
+    const int room = c.n_samples - j0;                                   // samples from the tile's first sample to the clip end (> 0)
+    int inside = room / G;                                               // full 8-row groups ending at or before the clip end
+    if (inside == kRawGroups - 1 && room >= (kRawGroups - 1) * G + (kRawRows - (kRawGroups - 1) * kRawGroup) * kHop)
+        inside = kRawGroups;                                             // the last group holds only 2 rows
+    r.hi = max(r.lo, min(r.need, inside));
     if ((c.wave_off & 3) != 0) r.hi = r.lo;                              // unaligned clip: no TMA at all
-    // the last group holds only 2 rows: it is inside iff those 2 rows are
-    if (r.hi == kRawGroups - 1 && r.need == kRawGroups &&
-        j0 + (int64_t)(kRawGroups - 1) * kRawGroup * kHop + (kRawRows - (kRawGroups - 1) * kRawGroup) * kHop <= c.n_samples)
-        r.hi = kRawGroups;
     return r;
 }
 
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
                 const ClipDesc c = p.clips[p.tile_clip[tile]];
                 const int f0 = (tile - c.tile0) * kTileM;
-                const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
+                const int j0 = f0 * kHop - kNfft / 2;
                 mbar_wait(raw_empty, (tl & 1) ^ 1);
                 trace(p.dbg, 3, tl, 0);
                 const RawPlan rp = raw_plan(c, j0, f0);
@@ -264,10 +266,10 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 if (nt < p.n_tiles) {
                     const ClipDesc cn = p.clips[p.tile_clip[nt]];
                     const int fn = (nt - cn.tile0) * kTileM;
-                    const int64_t jn = (int64_t)fn * kHop - kNfft / 2;
+                    const int jn = fn * kHop - kNfft / 2;
                     const RawPlan rn = raw_plan(cn, jn, fn);
                     if (rn.hi > rn.lo)
-                        bulk_prefetch_l2(p.wave + cn.wave_off + jn + (int64_t)rn.lo * kRawGroup * kHop,
+                        bulk_prefetch_l2(p.wave + cn.wave_off + jn + rn.lo * kRawGroup * kHop,
                                          (uint32_t)(min(rn.hi * kRawGroup, kRawRows) - rn.lo * kRawGroup) * kHop * 4);
                 }
                 trace(p.dbg, 3, tl, 1);
@@ -344,28 +346,28 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
             const ClipDesc c = p.clips[p.tile_clip[tile]];
             const int f0 = (tile - c.tile0) * kTileM;
-            const int64_t j0 = (int64_t)f0 * kHop - kNfft / 2;
+            const int j0 = f0 * kHop - kNfft / 2;
+            const RawPlan rp = raw_plan(c, j0, f0);                // before the wait: off the critical path
             mbar_wait(raw_full, tl & 1);
             if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 0);
-            {
+            if (rp.lo > 0 || rp.hi < rp.need) {
                 // clip edges: reflect padding (torch.stft centre=True) / ragged ends, by plain loads
-                const RawPlan rp = raw_plan(c, j0, f0);
-                const bool any = rp.lo > 0 || rp.hi < rp.need;
                 const float* x = p.wave + c.wave_off;
                 const int N = c.n_samples;
                 for (int g = 0; g < rp.need; ++g) {
                     if (g >= rp.lo && g < rp.hi) continue;
                     const int cnt = min(kRawGroup, kRawRows - g * kRawGroup) * kHop;
                     for (int i = xt; i < cnt; i += 512) {
-                        int64_t j = j0 + (int64_t)g * kRawGroup * kHop + i;
+                        int j = j0 + g * kRawGroup * kHop + i;
                         if (j < 0) j = -j;
-                        if (j >= N) j = 2 * (int64_t)(N - 1) - j;
+                        if (j >= N) j = 2 * (N - 1) - j;
                         j = j < 0 ? 0 : (j >= N ? N - 1 : j);
                         raw[g * kRawGroupPitch + i] = __ldg(x + j);
                     }
                 }
-                if (any) named_bar_sync(2, 512);
+                named_bar_sync(2, 512);
             }
+            if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 27);
             for (int ks = kpar; ks < kKSteps; ks += 2) {
                 const uint32_t it = tl * kKSteps + ks;
                 const int sa = it % kAStages;
@@ -395,6 +397,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                         lo[cidx] = rna_tf32(t[cidx] - hi[cidx]);
                     }
                 }
+                if (warp == 12 && lane == 0 && ks == 0) trace(p.dbg, 1, tl, 28);
                 // only the stores need the TMEM stage: everything above overlaps the MMAs in flight
                 mbar_wait(&a_empty[sa], ((it / kAStages) & 1) ^ 1);
                 tc_fence_after();
@@ -404,9 +407,11 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                     tmem_st8(tlane + sa * 32 + 8, lo);
                     tmem_st_wait();
                 }
+                if (warp == 12 && lane == 0 && ks == 0) trace(p.dbg, 1, tl, 29);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[sa]);
+                if (warp == 12 && lane == 0 && ks == 0) trace(p.dbg, 1, tl, 30);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(raw_empty);      // staged waveform no longer needed

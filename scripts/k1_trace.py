@@ -23,6 +23,7 @@ for tl in range(1, 6):
     print(f" xform: raw_full ok {x[0]}, empty ok ks0..4 {x[1:6].tolist()} ... ks24 {x[25]}, done {x[26]}")
     print(f" mma: tmem_empty ok {m[0]}, full ok ks0..4 {m[1:6].tolist()} ... ks24 {m[25]}, committed {m[26]}")
     print(f" epi: tmem_full ok {e[0]}, w4 chunks done {e[2]}, w4 flushed {e[3]}, barrier passed {e[4]}, end {e[1]} | w8 chunks done {e[5]}, w8 flushed {e[6]}")
+    print(f" xform first k-step: raw_full {x[0]}, edges staged {x[27]}, computed {x[28]}, stage free {x[1]}, stored {x[29]}, arrived {x[30]}")
     print(f" per-kstep mma deltas (ns): {np.diff(m[1:26]).tolist()}")
 tl = 3
 m, x, p = t[0, tl] - t0, t[1, tl] - t0, t[3, tl] - t0
