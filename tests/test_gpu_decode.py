@@ -312,3 +312,24 @@ def test_fuzz_ragged_plans_bit_exact(seed):
     pred = (np.round(pred * 2) / 2 if quant else 2.0 * pred).astype(np.float32)
     res, emis, codes = run_plan(pred, rows, mode, t_len)
     check_against_oracle(pred, rows, mode, t_len, res, emis, codes, f"fuzz{seed}")
+
+
+def test_emission_kernel_is_deterministic_and_exact_at_scale():
+    """4 440 full-width rows (10 per CTA at 3 CTAs/SM: every ring stage is recycled many times). The TMA
+    ring's producer/consumer hand-off is ordered only by mbarriers (compute-sanitizer's racecheck cannot
+    model that for bulk async copies and flags it), so check it the hard way: three runs must agree
+    bit for bit, and every emission must sit within the fp32 budget of the fp64 oracle."""
+    rng = np.random.default_rng(21)
+    T, V, L = 4440, 21129, 40
+    lab = _rand_rows(rng, 1, L, L, 402)[0]
+    pred = (2.0 * rng.standard_normal((T, V))).astype(np.float32)
+    pred[:, -1] = rng.uniform(-5, 5, size=T)
+    runs = []
+    for _ in range(3):
+        res, emis, _ = run_plan(pred, [lab], MODE_CTC, [T])
+        runs.append(emis[0])
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    e64, b64 = oracle.emission_ctc_f64(pred)
+    want = np.concatenate([b64, e64[:, lab - 1]], axis=1)
+    tol = emission_tolerance(pred[:, -1], True)[:, None]
+    assert np.all(np.abs(runs[0] - want) <= tol), float(np.abs(runs[0] - want).max())
