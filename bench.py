@@ -170,7 +170,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     import faulthandler
-    faulthandler.dump_traceback_later(420, exit=True)     # a hung collective must not eat the whole time budget
+    faulthandler.dump_traceback_later(900, exit=True)     # a hung collective must not eat the whole time budget
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
