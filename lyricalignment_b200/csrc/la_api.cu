@@ -140,8 +140,24 @@ int la_device_count(void) {
     return n;
 }
 
+static int plan_create_impl(la_plan** out, int mode, int n_utt, int V, const int32_t* h_t_len,
+                            const int32_t* h_l_len, const int32_t* h_labels, int device);
+
 int la_plan_create(la_plan** out, int mode, int n_utt, int V, const int32_t* h_t_len,
                    const int32_t* h_l_len, const int32_t* h_labels, int device) {
+    try {                                    // nothing may throw across the C ABI
+        return plan_create_impl(out, mode, n_utt, V, h_t_len, h_l_len, h_labels, device);
+    } catch (const std::bad_alloc&) {
+        return fail(LA_ERR_ALLOC, "out of host memory");
+    } catch (...) {
+        return fail(LA_ERR_ARG, "unexpected exception in la_plan_create");
+    }
+}
+
+}  // extern "C"
+
+static int plan_create_impl(la_plan** out, int mode, int n_utt, int V, const int32_t* h_t_len,
+                            const int32_t* h_l_len, const int32_t* h_labels, int device) {
     if (!out || n_utt < 0 || (n_utt > 0 && (!h_t_len || !h_l_len))) return fail(LA_ERR_ARG, "null argument");
     if (mode < 0 || mode > 2) return fail(LA_ERR_ARG, "mode must be LA_MODE_CTC/CE/LOGP");
     if ((mode == LA_MODE_CTC && V < 3) || V < 1) return fail(LA_ERR_ARG, "V too small for this mode");
@@ -229,6 +245,8 @@ int la_plan_create(la_plan** out, int mode, int n_utt, int V, const int32_t* h_t
     *out = P;
     return LA_OK;
 }
+
+extern "C" {
 
 void la_plan_destroy(la_plan* P) {
     if (!P) return;

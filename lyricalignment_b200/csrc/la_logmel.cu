@@ -607,8 +607,21 @@ static thread_local char g_lm_err[256];   // scratch for formatting; the message
 
 static inline size_t lm_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static int logmel_run_impl(const float* d_wave, float* d_out, const std::vector<la::ClipDesc>& clips_in, int n_groups,
+                           void* d_ws, size_t ws_bytes, cudaStream_t stream);
+
 static int logmel_run(const float* d_wave, float* d_out, const std::vector<la::ClipDesc>& clips_in, int n_groups,
                       void* d_ws, size_t ws_bytes, cudaStream_t stream) {
+    try {                                    // nothing may throw across the C ABI
+        return logmel_run_impl(d_wave, d_out, clips_in, n_groups, d_ws, ws_bytes, stream);
+    } catch (...) {
+        snprintf(g_lm_err, sizeof g_lm_err, "out of host memory");
+        LM_FAIL(LA_ERR_ALLOC);
+    }
+}
+
+static int logmel_run_impl(const float* d_wave, float* d_out, const std::vector<la::ClipDesc>& clips_in, int n_groups,
+                           void* d_ws, size_t ws_bytes, cudaStream_t stream) {
     using namespace la;
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
@@ -676,48 +689,58 @@ size_t la_logmel_workspace_bytes(int n_clips, int64_t total_samples) {
 
 int la_logmel(const float* d_wave, int batch, int64_t n_samples, int64_t wave_stride, float* d_out,
               int64_t out_stride, void* d_ws, void* stream) {
-    if (!d_wave || !d_out || !d_ws || batch < 0) { snprintf(g_lm_err, sizeof g_lm_err, "null argument"); LM_FAIL(LA_ERR_ARG); }
-    if (reinterpret_cast<uintptr_t>(d_wave) & 15) { snprintf(g_lm_err, sizeof g_lm_err, "waveform base must be 16-byte aligned"); LM_FAIL(LA_ERR_ARG); }
-    if (n_samples <= la::kNfft / 2) { snprintf(g_lm_err, sizeof g_lm_err, "reflect padding needs more than 200 samples"); LM_FAIL(LA_ERR_ARG); }
-    const int64_t F = n_samples / la::kHop;
-    if (out_stride < F || n_samples > INT32_MAX) { snprintf(g_lm_err, sizeof g_lm_err, "bad stride/size"); LM_FAIL(LA_ERR_ARG); }
-    std::vector<la::ClipDesc> clips((size_t)batch);
-    for (int b = 0; b < batch; ++b) {
-        clips[b].wave_off = (int64_t)b * wave_stride;
-        clips[b].out_off = (int64_t)b * la::kMels * out_stride;
-        clips[b].n_samples = (int32_t)n_samples;
-        clips[b].n_frames = (int32_t)F;
-        clips[b].out_stride = (int32_t)out_stride;
-        clips[b].group = 0;                       // one call == one global maximum (whisper semantics)
-        clips[b].tile0 = 0; clips[b].pad = 0;
+    try {
+        if (!d_wave || !d_out || !d_ws || batch < 0) { snprintf(g_lm_err, sizeof g_lm_err, "null argument"); LM_FAIL(LA_ERR_ARG); }
+        if (reinterpret_cast<uintptr_t>(d_wave) & 15) { snprintf(g_lm_err, sizeof g_lm_err, "waveform base must be 16-byte aligned"); LM_FAIL(LA_ERR_ARG); }
+        if (n_samples <= la::kNfft / 2) { snprintf(g_lm_err, sizeof g_lm_err, "reflect padding needs more than 200 samples"); LM_FAIL(LA_ERR_ARG); }
+        const int64_t F = n_samples / la::kHop;
+        if (out_stride < F || n_samples > INT32_MAX) { snprintf(g_lm_err, sizeof g_lm_err, "bad stride/size"); LM_FAIL(LA_ERR_ARG); }
+        std::vector<la::ClipDesc> clips((size_t)batch);
+        for (int b = 0; b < batch; ++b) {
+            clips[b].wave_off = (int64_t)b * wave_stride;
+            clips[b].out_off = (int64_t)b * la::kMels * out_stride;
+            clips[b].n_samples = (int32_t)n_samples;
+            clips[b].n_frames = (int32_t)F;
+            clips[b].out_stride = (int32_t)out_stride;
+            clips[b].group = 0;                       // one call == one global maximum (whisper semantics)
+            clips[b].tile0 = 0; clips[b].pad = 0;
+        }
+        return logmel_run(d_wave, d_out, clips, 1, d_ws, la_logmel_workspace_bytes(batch, (int64_t)batch * n_samples),
+                          static_cast<cudaStream_t>(stream));
+    } catch (...) {
+        snprintf(g_lm_err, sizeof g_lm_err, "out of host memory");
+        LM_FAIL(LA_ERR_ALLOC);
     }
-    return logmel_run(d_wave, d_out, clips, 1, d_ws, la_logmel_workspace_bytes(batch, (int64_t)batch * n_samples),
-                      static_cast<cudaStream_t>(stream));
 }
 
 int la_logmel_ragged(const float* d_wave, int n_clips, const int64_t* h_wave_off, const int32_t* h_n_samples,
                      float* d_out, const int64_t* h_out_off, const int32_t* h_out_stride, void* d_ws, void* stream) {
-    if (!d_wave || !d_out || !d_ws || n_clips < 0 || !h_wave_off || !h_n_samples || !h_out_off || !h_out_stride) {
-        snprintf(g_lm_err, sizeof g_lm_err, "null argument");
-        LM_FAIL(LA_ERR_ARG);
+    try {
+        if (!d_wave || !d_out || !d_ws || n_clips < 0 || !h_wave_off || !h_n_samples || !h_out_off || !h_out_stride) {
+            snprintf(g_lm_err, sizeof g_lm_err, "null argument");
+            LM_FAIL(LA_ERR_ARG);
+        }
+        if (reinterpret_cast<uintptr_t>(d_wave) & 15) { snprintf(g_lm_err, sizeof g_lm_err, "waveform base must be 16-byte aligned"); LM_FAIL(LA_ERR_ARG); }
+        std::vector<la::ClipDesc> clips((size_t)n_clips);
+        int64_t total = 0;
+        for (int c = 0; c < n_clips; ++c) {
+            if (h_n_samples[c] <= la::kNfft / 2) { snprintf(g_lm_err, sizeof g_lm_err, "clip %d too short for reflect padding", c); LM_FAIL(LA_ERR_ARG); }
+            clips[c].wave_off = h_wave_off[c];
+            clips[c].out_off = h_out_off[c];
+            clips[c].n_samples = h_n_samples[c];
+            clips[c].n_frames = h_n_samples[c] / la::kHop;
+            clips[c].out_stride = h_out_stride[c];
+            clips[c].group = c;                       // independent calls: one maximum per clip (batch size 1)
+            clips[c].tile0 = 0; clips[c].pad = 0;
+            if (clips[c].out_stride < clips[c].n_frames) { snprintf(g_lm_err, sizeof g_lm_err, "clip %d: out_stride < frames", c); LM_FAIL(LA_ERR_ARG); }
+            total += h_n_samples[c];
+        }
+        return logmel_run(d_wave, d_out, clips, std::max(n_clips, 1), d_ws, la_logmel_workspace_bytes(n_clips, total),
+                          static_cast<cudaStream_t>(stream));
+    } catch (...) {
+        snprintf(g_lm_err, sizeof g_lm_err, "out of host memory");
+        LM_FAIL(LA_ERR_ALLOC);
     }
-    if (reinterpret_cast<uintptr_t>(d_wave) & 15) { snprintf(g_lm_err, sizeof g_lm_err, "waveform base must be 16-byte aligned"); LM_FAIL(LA_ERR_ARG); }
-    std::vector<la::ClipDesc> clips((size_t)n_clips);
-    int64_t total = 0;
-    for (int c = 0; c < n_clips; ++c) {
-        if (h_n_samples[c] <= la::kNfft / 2) { snprintf(g_lm_err, sizeof g_lm_err, "clip %d too short for reflect padding", c); LM_FAIL(LA_ERR_ARG); }
-        clips[c].wave_off = h_wave_off[c];
-        clips[c].out_off = h_out_off[c];
-        clips[c].n_samples = h_n_samples[c];
-        clips[c].n_frames = h_n_samples[c] / la::kHop;
-        clips[c].out_stride = h_out_stride[c];
-        clips[c].group = c;                       // independent calls: one maximum per clip (batch size 1)
-        clips[c].tile0 = 0; clips[c].pad = 0;
-        if (clips[c].out_stride < clips[c].n_frames) { snprintf(g_lm_err, sizeof g_lm_err, "clip %d: out_stride < frames", c); LM_FAIL(LA_ERR_ARG); }
-        total += h_n_samples[c];
-    }
-    return logmel_run(d_wave, d_out, clips, std::max(n_clips, 1), d_ws, la_logmel_workspace_bytes(n_clips, total),
-                      static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
