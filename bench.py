@@ -374,7 +374,8 @@ def main():
             for b0 in range(0, n_calls, pool_n):
                 nb = min(pool_n, n_calls - b0)
                 mel, _, _ = LA.log_mel_spectrogram_ragged(wave_host[:pool_wave_end], w_off[:nb], n_samp[:nb])
-                res = la.align_clips(host[:int(offs[nb])], batch.t_len[:nb], [lab_for(b0 + i) for i in range(nb)])
+                res = la.align_clips(host[:int(offs[nb])], batch.t_len[:nb], [lab_for(b0 + i) for i in range(nb)],
+                                     staging_bytes=int(os.environ.get("BENCH_STAGING_MB", "0")) << 20)
                 tot += sum(len(u) for u in la.onoff_seconds(res))
             return tot
 
