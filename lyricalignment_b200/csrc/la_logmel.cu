@@ -521,12 +521,13 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
 // mel power -> log10(clamp 1e-10) -> max(x, gmax - 8) -> (x + 4) / 4 over the valid frames of every clip
 __global__ void logmel_finalize_kernel(const LogmelParams p) {
     const ClipDesc c = p.clips[blockIdx.y];
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;       // one frame column per thread, coalesced along f
+    if (f >= c.n_frames) return;
     const float gmax = log10f(fmaxf(__int_as_float(p.group_max[c.group]), 1e-10f));
     const float floor_v = gmax - 8.0f;
-    const int total = kMels * c.n_frames;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int m = i / c.n_frames, f = i - m * c.n_frames;
-        float* q = p.out + c.out_off + (int64_t)m * c.out_stride + f;
+    float* q = p.out + c.out_off + f;
+#pragma unroll 8
+    for (int m = 0; m < kMels; ++m, q += c.out_stride) {
         const float x = log10f(fmaxf(*q, 1e-10f));
         *q = (fmaxf(x, floor_v) + 4.0f) / 4.0f;
     }
@@ -666,8 +667,12 @@ static int logmel_run_impl(const float* d_wave, float* d_out, const std::vector<
     if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "smem attr: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
     const int ctas = la::g_logmel_ctas > 0 ? std::min(la::g_logmel_ctas, sms) : sms;
     logmel_kernel<<<std::min(n_tiles, ctas), kLogmelThreads, smem, stream>>>(p);
-    const int fx = std::max(1, std::min(64, (kMels * max_frames + 255) / 256));
-    logmel_finalize_kernel<<<dim3(fx, (unsigned)clips.size()), 256, 0, stream>>>(p);
+    for (size_t c0 = 0; c0 < clips.size(); c0 += 65535) {            // gridDim.y limit
+        LogmelParams q = p;
+        q.clips = p.clips + c0;
+        const unsigned ny = (unsigned)std::min<size_t>(65535, clips.size() - c0);
+        logmel_finalize_kernel<<<dim3((max_frames + 127) / 128, ny), 128, 0, stream>>>(q);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "launch: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
     return LA_OK;
