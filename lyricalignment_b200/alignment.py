@@ -138,10 +138,12 @@ def _run_device(plan: AlignPlan, logits2d: torch.Tensor, sil: torch.Tensor | Non
         logits2d = logits2d.clone()
     ld = logits2d.stride(0) if logits2d.shape[0] > 1 else max(logits2d.stride(0), plan.V)
     ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
-    first = torch.empty(max(plan.total_labels, 1), dtype=torch.int32, device=dev)
-    last = torch.empty(max(plan.total_labels, 1), dtype=torch.int32, device=dev)
-    score = torch.empty(max(plan.n_utt, 1), dtype=torch.float64, device=dev)
-    status = torch.empty(max(plan.n_utt, 1), dtype=torch.int32, device=dev)
+    # one packed result buffer -> one D2H: [score f64 x B | first i32 x L | last i32 x L | status i32 x B]
+    B, Ltot = max(plan.n_utt, 1), max(plan.total_labels, 1)
+    packed = torch.empty(8 * B + 4 * (2 * Ltot + B), dtype=torch.uint8, device=dev)
+    score = packed[:8 * B].view(torch.float64)
+    ints = packed[8 * B:].view(torch.int32)
+    first, last, status = ints[:Ltot], ints[Ltot:2 * Ltot], ints[2 * Ltot:2 * Ltot + B]
     stream = _stream_ptr(dev)
     if plan.mode == MODE_LOGP:
         _lib.check(lib.la_emit(plan.handle, logits2d.data_ptr(), ld, sil.data_ptr(), sil.stride(0),
@@ -151,8 +153,11 @@ def _run_device(plan: AlignPlan, logits2d: torch.Tensor, sil: torch.Tensor | Non
     else:
         _lib.check(lib.la_align(plan.handle, logits2d.data_ptr(), ld, ws.data_ptr(), first.data_ptr(),
                                 last.data_ptr(), score.data_ptr(), status.data_ptr(), stream), "la_align")
-    res = AlignResult(first.cpu().numpy()[:plan.total_labels], last.cpu().numpy()[:plan.total_labels],
-                      score.cpu().numpy()[:plan.n_utt], status.cpu().numpy()[:plan.n_utt], plan.l_len)
+    host = packed.cpu().numpy()
+    h_score = host[:8 * B].view(np.float64)
+    h_int = host[8 * B:].view(np.int32)
+    res = AlignResult(h_int[:plan.total_labels], h_int[Ltot:Ltot + plan.total_labels],
+                      h_score[:plan.n_utt], h_int[2 * Ltot:2 * Ltot + plan.n_utt], plan.l_len)
     return (res, ws) if keep_workspace else res
 
 
