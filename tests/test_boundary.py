@@ -86,3 +86,20 @@ def test_label_resolution_follows_numpy_indexing():
     assert _resolve_columns([np.array([0])], 10)[1].tolist() == [10]
     with pytest.raises(IndexError):
         _resolve_columns([np.array([11])], 10)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU: it times the reference's CPU path (the unmodified
+    reference where its tree is mounted, else the oracle port) and prints ONE JSON line."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "audio-s/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
