@@ -1,5 +1,6 @@
 // la_logmel.cu -- K1: Whisper-style 80-bin log-mel front end as a framed, windowed DFT on the
-// 5th-gen tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, fp32 accumulators in TMEM).
+// 5th-gen tensor cores (tcgen05.mma kind::f16, operands sliced on a fixed grid so that the leading
+// product chain is EXACT in the fp32 TMEM accumulator).
 //
 // Replaces whisper.audio.log_mel_spectrogram as called at module/align_model.py:84 (the
 // reference runs it on the CPU through torch.stft): hann(400, periodic) window, hop 160,
@@ -7,34 +8,53 @@
 // log10(clamp 1e-10), max(x, GLOBAL max - 8), (x + 4) / 4.
 //
 // Formulation. The Hann window is symmetric (w[n] = w[400-n], w[0] = 0), so with the folded
-// inputs  e[n] = x[n] + x[400-n],  o[n] = x[n] - x[400-n]  (n = 1..199; e[200] = x[200]):
-//     Re X[k] = sum_{n=1..200} e[n] * w[n] cos(2 pi k n / 400)
-//     Im X[k] = sum_{n=1..199} o[n] * (-w[n] sin(2 pi k n / 400))
-// i.e. two GEMMs [128 frames x 200] x [200 x 208] per tile -- half the FLOPs and half the basis
-// bytes of the plain [128 x 400] x [400 x 402] product. Precision: every operand is split
-// x = hi + lo with hi exactly representable in TF32; the kernel issues hi*hi + hi*lo + lo*hi
-// (the dropped lo*lo term is 2^-22 relative), which lands 1e-6..1e-5 from the fp64 oracle in
-// the log10 domain (single-pass TF32 would be 3e-1 off on tonal input).
+// inputs  e[n] = x[n] + x[400-n],  o[n] = x[n] - x[400-n]  (n = 0..207; rows 0 and 201.. of the
+// basis are zero, row 200 of the cosine basis is halved because e[200] = 2 x[200]):
+//     Re X[k] = sum_n e[n] * w[n] cos(2 pi k n / 400)        (pass 0)
+//     Im X[k] = sum_n o[n] * (-w[n] sin(2 pi k n / 400))     (pass 1)
+// i.e. two GEMMs [128 frames x 208] x [208 x 208] per tile, run one after the other on the same
+// pair of TMEM accumulators.
+//
+// Precision (round 2). The tensor core's fp32 accumulate TRUNCATES (scripts/emulate_k1_precision.py),
+// so round 1's 75-deep 3xTF32 chain carried a biased error proportional to the PARTIAL sums, which for
+// a weak bin next to a strong one are far larger than the result (worst cell 3.3e-4 in log10 units).
+// Here every operand is sliced on a fixed grid instead (scripts/emulate_k1_precision_r2.py):
+//     T  = fold * 2^14 / S                S = power of two > 2 max|x| over the tile, so |T| < 2^14
+//     A1 = T rounded to a multiple of 64  (8 significant bits: exact in fp16)
+//     A2 = fp16(T - A1),  A3 = fp16(T - A1 - A2)          (11 bits each; |A3| < 2^-7, mostly normal)
+// and the same for the basis (B1, B2, B3 from 2^14 w[n] cos|sin, sliced on the host in fp64). Then
+//     Acc0 = sum A1*B1                      each product is 2^12 x an integer < 2^16 and there are 208 of
+//                                           them: every partial sum has < 24 significant bits, so the chain
+//                                           is EXACT in fp32 whatever the rounding mode;
+//     Acc1 = sum A3*B1 + A1*B3 + A2*B2 + A2*B1 + A1*B2      terms <= 2^-9 of Acc0's: truncation there
+//                                           is 2^-9 of what it was;
+//     X    = 2^-28 S (Acc0 + Acc1)          one fp32 round-to-nearest add in the epilogue.
+// Dropped: A2*B3 + A3*B2 + A3*B3 (2^-30 of full scale). kind::f16 has K = 16 at twice the TF32 rate, so
+// the 6 x 13 MMAs per pass cost the tensor pipe what round 1's 3 x 25 did. Emulated worst cell
+// 6e-6 (the reference's own fp32 torch.stft: 3e-5 .. 8e-5), measured: profiles/logmel_precision_r2.txt.
 //
 // One persistent CTA per SM (896 threads), 128-frame tiles, warp-specialised:
 //   warp 0       producer: 1-D TMA bulk copies of the tile's waveform (17 copies of 8 hop rows into a
-//                staging area padded by 8 floats per copy) and of the constant basis blocks (26 KB per
-//                k-step, L2-resident) into a 5-deep shared-memory ring;
-//   warps 1, 2   MMA issuers (one elected lane each: Re and Im accumulators, 75 tcgen05.mma per tile
-//                each, A operand from TMEM, B from shared memory); warp 1 also owns the TMEM allocation;
-//   warps 12..27 transform: staged waveform -> folded, hi/lo-split A operands written straight into
-//                TMEM with tcgen05.st (thread = frame row = TMEM lane; bank-conflict-free rotated
-//                reads); two warp sets ping-pong the k-steps through a 3-deep TMEM ring;
+//                staging area padded by 8 floats per copy) and of the constant basis blocks (3 fp16
+//                slices = 19.5 KB per k-step, L2-resident) into a 5-deep shared-memory ring;
+//   warps 1, 2   MMA issuers (one elected lane each): warp 1 owns Acc0 (1 MMA per k-step), warp 2 owns
+//                Acc1 (5 MMAs per k-step, operands of the next k-step awaited before the last one is
+//                issued so the pipe never drains); A from TMEM, B from shared memory; warp 1 also owns
+//                the TMEM allocation. Each accumulator is written by ONE thread in program order, so
+//                results are deterministic;
+//   warps 12..27 transform: staged waveform -> tile scale -> folded, sliced A operands written straight
+//                into TMEM with tcgen05.st (thread = frame row = TMEM lane; bank-conflict-free rotated
+//                reads); four warp sets take every 4th k-step through a 4-deep TMEM ring;
 //   warps 4..11  epilogue (two warps per TMEM lane quarter, bins split in two): TMEM -> registers,
-//                power, sparse mel projection as straight-line code from a generated compile-time
-//                table (each FFT bin feeds <= 2 adjacent triangular filters), coalesced stores of the
-//                mel power, running max.
-// TMEM: columns [0,416) hold the Re/Im accumulators, [416,512) the A ring. Clip-edge hop-row groups
-// (reflect padding, ragged ends) are staged by the transform warps with plain loads instead of
-// TMA. A second small kernel applies log10, the max-8 floor and (x+4)/4.
-// History of the tuning (profiles/k1_tuning_r1.md): SS-mode operands were shared-memory-bandwidth
-// bound, a 3200-instruction unrolled epilogue was instruction-fetch bound, a single MMA issuer left
-// the tensor pipe idle ~30 % of the time.
+//                (Acc0 + Acc1)^2, sparse mel projection as straight-line code from a generated
+//                compile-time table (each FFT bin feeds <= 2 adjacent triangular filters). Pass 0 parks
+//                the Re part of the mel sums in shared memory, pass 1 adds the Im part, applies the tile
+//                scale and log10 and stores (x + 4) / 4 directly, tracking the group maximum and the
+//                tile minimum.
+// TMEM: columns [0,208) Acc0, [208,416) Acc1, [416,512) the A ring (4 stages x 3 planes x 8 columns).
+// Clip-edge hop-row groups (reflect padding, ragged ends) are staged by the transform warps with plain
+// loads instead of TMA. logmel_floor_kernel then applies the max-8 floor, touching only the tiles
+// whose minimum lies below it (digital silence, fades).
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -43,6 +63,8 @@
 #include <cstring>
 #include <mutex>
 #include <vector>
+
+#include <cuda_fp16.h>
 
 #include "../../include/lyricalign.h"
 #include "la_common.cuh"
@@ -53,24 +75,30 @@ namespace la {
 constexpr int kNfft = 400, kHop = 160, kMels = 80, kBins = 201;
 constexpr int kTileM = 128;                 // frames per tile
 constexpr int kNpad = 208;                  // 201 bins padded to a multiple of 16
-constexpr int kKSteps = 25;                 // 200 folded samples / 8 (UMMA_K for tf32)
+constexpr int kKSteps = 13;                 // per pass: 208 folded samples / 16 (UMMA_K for f16)
+constexpr int kIters = 2 * kKSteps;         // k-steps per tile: pass 0 (Re) then pass 1 (Im)
 constexpr int kRawRows = 130;               // hop rows staged per tile
 constexpr int kRawGroup = 8;                // hop rows per bulk copy (the TMA request rate, ~35 ns each, is the limit)
 constexpr int kRawGroupPitch = kRawGroup * kHop + 8;   // floats: +8 per group -> thread-per-row reads hit 32 banks
 constexpr int kRawGroups = (kRawRows + kRawGroup - 1) / kRawGroup;   // 17
 constexpr int kRawBytes = kRawGroups * kRawGroupPitch * 4;           // 87584
 constexpr int kBLbo = (kNpad / 8) * 128;    // 3328 bytes between K-adjacent core matrices of the basis
-constexpr int kBBytes = 2 * kBLbo;          // 6656: one basis operand (hi or lo) of one k-step
-constexpr int kBStageBytes = 4 * kBBytes;   // 26624: [C_hi C_lo S_hi S_lo]
+constexpr int kBBytes = 2 * kBLbo;          // 6656: one fp16 slice of one k-step [ki 2][ni 26][8 bins][8 samples]
+constexpr int kSlices = 3;
+constexpr int kBStageBytes = kSlices * kBBytes;   // 19968: [B1 B2 B3]
 constexpr int kBStages = 5;
-constexpr int kAStages = 3;                 // A operands live in TMEM: 4 planes x 8 columns per stage
+constexpr int kAStages = 4;                 // A operands live in TMEM: 3 planes x 8 columns per stage
+constexpr int kAStageCols = 24;
 constexpr int kACol0 = 2 * kNpad;           // TMEM columns [0,416) accumulators, [416,512) A ring
-constexpr int kXformWarps = 16;             // warps 12..27: {even,odd k-steps} x {even,odd planes} x 4 lane quarters
+constexpr int kXformWarps = 16;             // warps 12..27: 4 sets (k-step mod 4) x 4 lane quarters
 constexpr int kEpiWarps = 8;                // warps 4..11: two per TMEM lane quarter, bins split at kSplit
 constexpr int kSplit = LA_MEL_SPLIT;        // bins [0, 96) -> warps 4..7, [96, 201) -> warps 8..11
 constexpr int kLogmelThreads = 896;
 constexpr uint32_t kTmemCols = 512;
-static_assert(kACol0 + kAStages * 32 <= 512, "TMEM columns");
+constexpr int kPartBytes = kMels * kTileM * 4;          // Re part of the mel sums between the passes
+constexpr int kSharedBytes = 2 * 2 * kTileM * 4;        // the two filters fed by both bin halves, double-buffered
+constexpr int kMiscBytes = 256;                         // per-warp maxima [2][16], tile exponent [2]
+static_assert(kACol0 + kAStages * kAStageCols <= 512, "TMEM columns");
 
 struct ClipDesc {
     int64_t wave_off;   // float offset of the clip's first sample
@@ -90,9 +118,10 @@ struct LogmelParams {
     const int32_t* tile_clip;     // [n_tiles]
     int n_tiles;
     int n_clips;
-    const float* basis;           // [25][even: C_hi, C_lo | odd: S_hi, S_lo] canonical UMMA layout
+    const __half* basis;          // [pass 2][k-step 13][slice 3] canonical UMMA K-major blocks
     int* group_max;               // running maxima of the mel power (bit pattern of a float >= 0)
-    int dbg;                      // LA_LOGMEL_DBG bisect knobs (perf triage only): 1 skip epilogue math, 2 skip transform math, 4 skip basis loads
+    int* tile_min;                // per-tile minima of the mel power (same encoding)
+    int dbg;                      // LA_LOGMEL_DBG: 8 = CTA 0 timestamps its first tiles (perf triage), 16 = swap the fp16 pair order (bring-up)
 };
 
 // LA_LOGMEL_DBG & 8: CTA 0 timestamps its first 8 tiles (perf triage only)
@@ -104,8 +133,6 @@ __device__ __forceinline__ void trace(int dbg, int role, uint32_t tl, int ev) {
         g_trace[(role * 8 + tl) * 32 + ev] = t;
     }
 }
-
-
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -119,30 +146,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
+// A operand from TMEM (128 lanes x 8 columns = 16 fp16 along K), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// A operand from TMEM (128 lanes x 8 columns of tf32), B from shared memory
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
-                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
-                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -167,24 +183,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-// cute::UMMA::InstrDescriptor: D = f32 (1 @ [4,6)), A = B = tf32 (2 @ [7,10), [10,13)), both
+// cute::UMMA::InstrDescriptor: D = f32 (1 @ [4,6)), A = B = f16 (0 @ [7,10), [10,13)), both
 // K-major, N>>3 @ [17,23), M>>4 @ [24,29).
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNpad >> 3) << 17) |
+constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kNpad >> 3) << 17) |
                             ((uint32_t)(kTileM >> 4) << 24);
-
-__device__ __forceinline__ int float_to_ordered(float v) {
-    const int i = __float_as_int(v);
-    return i >= 0 ? i : i ^ 0x7fffffff;
-}
-__device__ __forceinline__ float ordered_to_float(int k) {
-    return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
-}
-
-__device__ __forceinline__ float rna_tf32(float x) {      // round-to-nearest TF32 (10 explicit mantissa bits)
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 
 // How the hop-row groups (8 rows = 1280 samples each) of a tile are staged. Computed once per tile:
 // groups [0, need) are needed at all (the rest feed only frames past the clip end), of those the
@@ -209,14 +211,27 @@ __device__ __forceinline__ RawPlan raw_plan(const ClipDesc& c, int j0, int f0) {
     return r;
 }
 
+__device__ __forceinline__ float max4abs(const float4 v, float m) {
+    return fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fmaxf(fabsf(v.y), fabsf(v.z)), fabsf(v.w)));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {       // element with the lower K index in the low half
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* bstages = smem;
     float* raw = reinterpret_cast<float*>(smem + kBStages * kBStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBStages * kBStageBytes + kRawBytes);
+    float* part = reinterpret_cast<float*>(smem + kBStages * kBStageBytes + kRawBytes);          // [80][128]
+    float* shared2 = part + kMels * kTileM;                                                       // [2][2][128]
+    float* wmax = shared2 + 2 * 2 * kTileM;                                                       // [2][16]
+    int* tile_e = reinterpret_cast<int*>(wmax + 32);                                              // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBStages * kBStageBytes + kRawBytes + kPartBytes +
+                                                 kSharedBytes + kMiscBytes);
     uint64_t* b_full = bars;                         // [kBStages] basis block landed (tx)
     uint64_t* b_empty = b_full + kBStages;           // [kBStages] MMAs that read it retired
-    uint64_t* a_full = b_empty + kBStages;           // [kAStages] 8 transform warps stored their planes
+    uint64_t* a_full = b_empty + kBStages;           // [kAStages] 4 transform warps stored their planes
     uint64_t* a_empty = a_full + kAStages;           // [kAStages] MMAs that read it retired
     uint64_t* raw_full = a_empty + kAStages;
     uint64_t* raw_empty = raw_full + 1;
@@ -228,7 +243,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
 
     if (tid == 0) {
         for (int s = 0; s < kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2); }      // 2 MMA issuers
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&a_full[s], kXformWarps / 2); mbar_init(&a_empty[s], 2); }
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 2); }
         mbar_init(raw_full, 1);
         mbar_init(raw_empty, kXformWarps);
         mbar_init(tmem_full, 2);
@@ -273,64 +288,80 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                                          (uint32_t)(min(rn.hi * kRawGroup, kRawRows) - rn.lo * kRawGroup) * kHop * 4);
                 }
                 trace(p.dbg, 3, tl, 1);
-                for (int ks = 0; ks < kKSteps; ++ks, ++it) {
+                for (int i = 0; i < kIters; ++i, ++it) {
                     const int s = it % kBStages;
                     mbar_wait(&b_empty[s], ((it / kBStages) & 1) ^ 1);
-                    trace(p.dbg, 3, tl, 2 + ks);
-                    if (p.dbg & 4) { mbar_arrive(&b_full[s]); continue; }
+                    trace(p.dbg, 3, tl, 2 + i);
                     mbar_arrive_expect_tx(&b_full[s], kBStageBytes);
                     bulk_g2s(bstages + s * kBStageBytes,
-                             reinterpret_cast<const unsigned char*>(p.basis) + (size_t)ks * kBStageBytes, kBStageBytes,
+                             reinterpret_cast<const unsigned char*>(p.basis) + (size_t)i * kBStageBytes, kBStageBytes,
                              &b_full[s]);
                 }
             }
         }
     } else if (warp == 1 || warp == 2) {
         // =============================== MMA issuers =======================================
-        // Two issuing threads: warp 1 accumulates Re (even planes x cos basis), warp 2 Im (odd planes x
-        // sin basis). tcgen05.mma issue is back-pressured by the tensor pipe, so a single issuer's
-        // per-k-step bookkeeping (barrier waits, commits) left the pipe idle ~30 % of the time;
-        // with two, one thread's bookkeeping overlaps the other's MMAs. Each accumulator is written
-        // by one thread in program order, so results stay deterministic.
+        // warp 1: Acc0 += A1*B1 (the exact chain); warp 2: Acc1 += the five cross terms. tcgen05.mma issue is
+        // back-pressured by the tensor pipe; warp 2 waits for the NEXT k-step's operands between its 4th
+        // and 5th MMA, so its barrier bookkeeping overlaps MMAs that are still queued.
         if (lane == 0) {
-            const int im = warp == 2 ? 1 : 0;
-            const uint32_t d_acc = tmem_base + (im ? kNpad : 0);
-            const uint32_t ta0 = tmem_base + kACol0 + (im ? 16 : 0);               // hi plane; lo plane at +8
-            const uint64_t bd_hi0 = umma_desc(smem_u32(bstages) + (im ? 2 * kBBytes : 0), kBLbo, 128);
-            const uint64_t bd_lo0 = umma_desc(smem_u32(bstages) + (im ? 3 * kBBytes : kBBytes), kBLbo, 128);
+            const bool cross = warp == 2;
+            const uint32_t d_acc = tmem_base + (cross ? kNpad : 0);
+            const uint32_t ta0 = tmem_base + kACol0;
+            const uint32_t bs0 = smem_u32(bstages);
             uint32_t it = 0, tl = 0;
+            bool ready = false;                       // operands of iteration `it` already awaited
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
-                mbar_wait(tmem_empty, (tl & 1) ^ 1);       // epilogue of the previous tile drained TMEM
-                tc_fence_after();
-                if (!im) trace(p.dbg, 0, tl, 0);
-                for (int ks = 0; ks < kKSteps; ++ks, ++it) {
-                    const int sb = it % kBStages, sa = it % kAStages;
-                    mbar_wait(&b_full[sb], (it / kBStages) & 1);
-                    mbar_wait(&a_full[sa], (it / kAStages) & 1);
+                for (int pass = 0; pass < 2; ++pass) {
+                    const uint32_t ph = 2 * tl + pass;
+                    mbar_wait(tmem_empty, (ph & 1) ^ 1);   // epilogue of the previous pass drained TMEM
                     tc_fence_after();
-                    if (!im) trace(p.dbg, 0, tl, 1 + ks);
-                    const uint32_t ta = ta0 + sa * 32;
-                    const uint64_t b_hi = bd_hi0 + (uint64_t)(sb * (kBStageBytes >> 4));   // start-address field += stage
-                    const uint64_t b_lo = bd_lo0 + (uint64_t)(sb * (kBStageBytes >> 4));
-                    umma_tf32_ts(d_acc, ta, b_lo, kIdesc, ks > 0 ? 1u : 0u);   // small terms first
-                    umma_tf32_ts(d_acc, ta + 8, b_hi, kIdesc, 1u);
-                    umma_tf32_ts(d_acc, ta, b_hi, kIdesc, 1u);
-                    umma_commit(&a_empty[sa]);
-                    umma_commit(&b_empty[sb]);
+                    if (cross) trace(p.dbg, 0, tl, pass ? 29 : 0);
+                    for (int ks = 0; ks < kKSteps; ++ks, ++it) {
+                        const int sb = it % kBStages, sa = it % kAStages;
+                        if (!ready) {
+                            mbar_wait(&b_full[sb], (it / kBStages) & 1);
+                            mbar_wait(&a_full[sa], (it / kAStages) & 1);
+                            tc_fence_after();
+                        }
+                        ready = false;
+                        if (cross) trace(p.dbg, 0, tl, 1 + pass * kKSteps + ks);
+                        const uint32_t a1 = ta0 + sa * kAStageCols, a2 = a1 + 8, a3 = a1 + 16;
+                        const uint64_t b1 = umma_desc(bs0 + sb * kBStageBytes, kBLbo, 128);
+                        const uint64_t b2 = umma_desc(bs0 + sb * kBStageBytes + kBBytes, kBLbo, 128);
+                        const uint64_t b3 = umma_desc(bs0 + sb * kBStageBytes + 2 * kBBytes, kBLbo, 128);
+                        if (!cross) {
+                            umma_f16_ts(d_acc, a1, b1, kIdesc, ks > 0 ? 1u : 0u);
+                        } else {
+                            umma_f16_ts(d_acc, a3, b1, kIdesc, ks > 0 ? 1u : 0u);   // small terms first
+                            umma_f16_ts(d_acc, a1, b3, kIdesc, 1u);
+                            umma_f16_ts(d_acc, a2, b2, kIdesc, 1u);
+                            umma_f16_ts(d_acc, a2, b1, kIdesc, 1u);
+                            const uint32_t nx = it + 1;
+                            if (nx < (uint32_t)kIters * (tl + 1) || tile + (int)gridDim.x < p.n_tiles) {
+                                mbar_wait(&b_full[nx % kBStages], (nx / kBStages) & 1);
+                                mbar_wait(&a_full[nx % kAStages], (nx / kAStages) & 1);
+                                tc_fence_after();
+                                ready = true;
+                            }
+                            umma_f16_ts(d_acc, a1, b2, kIdesc, 1u);
+                        }
+                        umma_commit(&a_empty[sa]);
+                        umma_commit(&b_empty[sb]);
+                    }
+                    umma_commit(tmem_full);
+                    if (cross) trace(p.dbg, 0, tl, 27 + pass);
                 }
-                umma_commit(tmem_full);
-                if (!im) trace(p.dbg, 0, tl, 26);
             }
         }
     } else if (warp >= 12) {
         // ====================== transform: staged waveform -> A operands in TMEM =============
-        // Thread = frame row (TMEM lane). Warps 12..15 produce the even planes (x[n] + x[400-n]),
-        // warps 16..19 the odd ones (x[n] - x[400-n]); both split hi/lo and tcgen05.st 8 columns
-        // per plane. Sample s of the tile sits at raw[s + 8 * (s / 1280)] (8 hop rows per bulk
-        // copy, 8 floats of padding between copies). Lane l reads its 8 samples rotated by l & 7,
-        // which makes every LDS hit 32 distinct banks; three select stages undo the rotation.
-        const bool odd = (warp - 12) & 4;          // warps 12-15, 20-23: even planes; 16-19, 24-27: odd planes
-        const int kpar = warp >= 20 ? 1 : 0;       // which k-steps this warp serves (two warp sets ping-pong)
+        // Thread = frame row (TMEM lane). Warp set s = (warp - 12) / 4 serves the k-steps with
+        // (global k-step index) % 4 == s, i.e. always TMEM stage s. Sample j of the tile sits at
+        // raw[j + 8 * (j / 1280)] (8 hop rows per bulk copy, 8 floats of padding between copies). Lane l
+        // reads each 8-sample window rotated by l & 7, which makes every LDS hit 32 distinct banks;
+        // three select stages undo the rotation.
+        const int set = (warp - 12) >> 2;
         const int q = warp & 3;                    // TMEM lane quarter == warp % 4
         const int r = q * 32 + lane;
         const int xt = tid - 384;
@@ -341,7 +372,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
         const float* row_d0 = raw + r * kHop + 8 * (r >> 3);          // hop-row offset 0, 1, 2 of frame r
         const float* row_d1 = raw + r * kHop + 8 * ((r + 1) >> 3);
         const float* row_d2 = raw + r * kHop + 8 * ((r + 2) >> 3);
-        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + kACol0 + (odd ? 16 : 0);
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + kACol0 + set * kAStageCols;
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
             const ClipDesc c = p.clips[p.tile_clip[tile]];
@@ -350,6 +381,8 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             const RawPlan rp = raw_plan(c, j0, f0);                // before the wait: off the critical path
             mbar_wait(raw_full, tl & 1);
             if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 0);
+            // ---- tile scale: largest |sample| over everything a stored frame of this tile reads ----
+            float m = 0.f;
             if (rp.lo > 0 || rp.hi < rp.need) {
                 // clip edges: reflect padding (torch.stft centre=True) / ragged ends, by plain loads
                 const float* x = p.wave + c.wave_off;
@@ -362,28 +395,49 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                         if (j < 0) j = -j;
                         if (j >= N) j = 2 * (N - 1) - j;
                         j = j < 0 ? 0 : (j >= N ? N - 1 : j);
-                        raw[g * kRawGroupPitch + i] = __ldg(x + j);
+                        const float v = __ldg(x + j);
+                        raw[g * kRawGroupPitch + i] = v;
+                        m = fmaxf(m, fabsf(v));
                     }
                 }
-                named_bar_sync(2, 512);
             }
-            if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 27);
-            for (int ks = kpar; ks < kKSteps; ks += 2) {
-                const uint32_t it = tl * kKSteps + ks;
-                const int sa = it % kAStages;
-                float hi[8], lo[8];
-                if (!(p.dbg & 2)) {
+            for (int g = rp.lo; g < rp.hi; ++g) {
+                const int cnt = min(kRawGroup, kRawRows - g * kRawGroup) * kHop;
+                const float4* src = reinterpret_cast<const float4*>(raw + g * kRawGroupPitch);
+                for (int i = xt; i < cnt / 4; i += 512) m = max4abs(src[i], m);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) wmax[(tl & 1) * 16 + (warp - 12)] = m;
+            named_bar_sync(2, 512);                                 // staging complete, per-warp maxima visible
+            m = wmax[(tl & 1) * 16 + (lane & 15)];
+#pragma unroll
+            for (int o = 8; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            // S = 2^(ex - 125) > 2 max|x| >= |fold|; T = fold * 2^14 / S; X = acc * S * 2^-28
+            int ex = (int)(__float_as_uint(m) >> 23);
+            ex = min(max(ex, 27), 250);
+            const float scale_t = __uint_as_float((uint32_t)(266 - ex) << 23);
+            if (xt == 0) tile_e[tl & 1] = ex;
+            if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 1);
+            const uint32_t it0 = tl * kIters;
+            for (uint32_t it = it0 + ((set - it0) & 3u); it < it0 + kIters; it += 4) {
+                const int local = (int)(it - it0);
+                const int pass = local >= kKSteps ? 1 : 0;
+                const int ks = local - pass * kKSteps;
+                uint32_t pk[24];                                     // [plane 3][column 8], two fp16 per column
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n0 = ks * 16 + h * 8;                  // n = n0 + jj in 0..207
+                    const float* fwd_row = (n0 >= kHop ? row_d1 : row_d0) + n0;   // 8-aligned windows never straddle 160
                     float v[8];
-                    const int n0 = ks * 8 + 1;                           // n = n0 + jj in 1..200
-                    const float* rev_row = (kNfft - n0 - 7 >= 2 * kHop) ? row_d2 : row_d1;   // m = 400 - n: 8-aligned windows never straddle 320
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int n = n0 + jj[j];
-                        const float fwd = (n >= kHop ? row_d1 : row_d0)[n];
-                        const float rev = rev_row[kNfft - n];
-                        v[j] = odd ? fwd - rev : fwd + rev;              // n = 200: e = 2 x[200] (basis row halved), o = 0
+                        const int mrev = kNfft - n0 - jj[j];         // 193..400
+                        const float fwd = fwd_row[jj[j]];
+                        const float rev = (mrev >= 2 * kHop ? row_d2 : row_d1)[mrev];
+                        v[j] = pass ? fwd - rev : fwd + rev;          // n = 200: e = 2 x[200] (basis row halved), o = 0
                     }
-                    // undo the rotation: w[c] = v[(c - rot) & 7]
+                    // undo the rotation: t[c] = v[(c - rot) & 7]
                     float t[8];
 #pragma unroll
                     for (int cidx = 0; cidx < 8; ++cidx) t[cidx] = (rot & 1) ? v[(cidx + 7) & 7] : v[cidx];
@@ -391,122 +445,177 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                     for (int cidx = 0; cidx < 8; ++cidx) v[cidx] = (rot & 2) ? t[(cidx + 6) & 7] : t[cidx];
 #pragma unroll
                     for (int cidx = 0; cidx < 8; ++cidx) t[cidx] = (rot & 4) ? v[(cidx + 4) & 7] : v[cidx];
+                    if (ks == 0 && h == 0) t[0] = 0.f;                // n = 0 pairs x[0] with x[400], which the last frame may not have staged (basis row 0 is zero)
+                    // slice on the fixed grid: A1 = multiple of 64, A2 = fp16(T - A1), A3 = fp16(T - A1 - A2)
 #pragma unroll
-                    for (int cidx = 0; cidx < 8; ++cidx) {
-                        hi[cidx] = rna_tf32(t[cidx]);
-                        lo[cidx] = rna_tf32(t[cidx] - hi[cidx]);
+                    for (int cidx = 0; cidx < 8; cidx += 2) {
+                        const float T0 = t[cidx] * scale_t, T1 = t[cidx + 1] * scale_t;
+                        const float A0 = (T0 + 805306368.f) - 805306368.f;          // 1.5 * 2^29: ulp 64, round to nearest even
+                        const float A1 = (T1 + 805306368.f) - 805306368.f;
+                        const float R0 = T0 - A0, R1 = T1 - A1;                       // exact
+                        const __half2 h2 = __floats2half2_rn(R0, R1);
+                        const float2 f2 = __half22float2(h2);
+                        const int col = h * 4 + (cidx >> 1);
+                        if (p.dbg & 16) {
+                            pk[col] = pack_h2(A1, A0);
+                            pk[8 + col] = pack_h2(f2.y, f2.x);
+                            pk[16 + col] = pack_h2(R1 - f2.y, R0 - f2.x);
+                        } else {
+                            pk[col] = pack_h2(A0, A1);
+                            pk[8 + col] = *reinterpret_cast<const uint32_t*>(&h2);
+                            pk[16 + col] = pack_h2(R0 - f2.x, R1 - f2.y);
+                        }
                     }
                 }
-                if (warp == 12 && lane == 0 && ks == 0) trace(p.dbg, 1, tl, 28);
                 // only the stores need the TMEM stage: everything above overlaps the MMAs in flight
-                mbar_wait(&a_empty[sa], ((it / kAStages) & 1) ^ 1);
+                mbar_wait(&a_empty[set], ((it >> 2) & 1) ^ 1);
                 tc_fence_after();
-                if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 1 + ks);
-                if (!(p.dbg & 2)) {
-                    tmem_st8(tlane + sa * 32, hi);
-                    tmem_st8(tlane + sa * 32 + 8, lo);
+                if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 2 + (local >> 2));
+                {
+                    uint32_t pl[8];
+#pragma unroll
+                    for (int pln = 0; pln < 3; ++pln) {
+#pragma unroll
+                        for (int cidx = 0; cidx < 8; ++cidx) pl[cidx] = pk[pln * 8 + cidx];
+                        tmem_st8(tlane + pln * 8, pl);
+                    }
                     tmem_st_wait();
                 }
-                if (warp == 12 && lane == 0 && ks == 0) trace(p.dbg, 1, tl, 29);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[sa]);
-                if (warp == 12 && lane == 0 && ks == 0) trace(p.dbg, 1, tl, 30);
+                if (lane == 0) mbar_arrive(&a_full[set]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(raw_empty);      // staged waveform no longer needed
-            if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 26);
+            if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 30);
         }
     } else if (warp >= 4 && warp < 12) {
-        // ====================== epilogue: power -> mel, straight out of TMEM (256 threads) ====
-        // Two warps share each TMEM lane quarter and split the 201 bins at kSplit. Exactly two
-        // filters (ms, ms + 1, ms = first filter fed by bin kSplit) receive power from both sides.
-        // The mel POWER is stored; log10 / floor / scaling happen in logmel_finalize_kernel (max is
-        // monotone under log10). The loop body is kept small on purpose: the first version unrolled
-        // to 3200 instructions and spent its time in instruction fetch.
+        // ====================== epilogue: (Acc0 + Acc1)^2 -> mel, straight out of TMEM (256 threads) ====
+        // Two warps share each TMEM lane quarter and split the 201 bins at kSplit. Exactly two filters
+        // (ms, ms + 1, ms = first filter fed by bin kSplit) receive power from both sides: the high half
+        // parks its share in `shared2`, the low half finishes and stores them after one named barrier.
+        // The loop body is kept small on purpose: the first version unrolled to 3200 instructions and
+        // spent its time in instruction fetch.
         const int half = warp >= 8 ? 1 : 0;
         const int wq = warp & 3;                   // TMEM lane quarter == warp % 4
         const int row = wq * 32 + lane;
         constexpr int ms = LA_MEL_MS;
+        float r_ms0 = 0.f, r_ms1 = 0.f;            // low half: Re part of the two shared filters
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
             const ClipDesc c = p.clips[p.tile_clip[tile]];
             const int f0 = (tile - c.tile0) * kTileM;
-            mbar_wait(tmem_full, tl & 1);
-            tc_fence_after();
-            if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 0);
             const int f = f0 + row;
             const bool valid = f < c.n_frames;
             const int64_t ostride = c.out_stride;
             float* outp = p.out + c.out_off + f;
-            float* optr = outp + (half ? ms : 0) * ostride;   // where the filter held in a0 will be stored
-            float mx = 0.f;
-            float a0 = 0.f, a1 = 0.f;
-            auto flush = [&]() {                    // the filter held in a0 is complete: store its power
-                if (valid) { *optr = a0; mx = fmaxf(mx, a0); }   // rows past the clip's last frame hold garbage
-                optr += ostride;
-                a0 = a1; a1 = 0.f;
-            };
-            const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
-            uint32_t re[16], im[16];
-            auto release_tmem = [&]() {             // this warp's share of TMEM is in registers
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_empty);
-            };
-            // Straight-line code: the filterbank is a compile-time table (la_mel_table.inc), so the
-            // weights are FFMA immediates and the flush points are static. The first bin of each
-            // half never flushes (the accumulators start empty on that filter).
+            float mx = 0.f, mn = INFINITY;
+            float* sh2 = shared2 + (tl & 1) * 2 * kTileM + row;
+            for (int pass = 0; pass < 2; ++pass) {
+                const uint32_t ph = 2 * tl + pass;
+                mbar_wait(tmem_full, ph & 1);
+                tc_fence_after();
+                if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 2 * pass);
+                const float sc = __uint_as_float((uint32_t)(tile_e[tl & 1] - 26) << 23);    // S * 2^-28
+                const float sc2 = sc * sc;
+                int64_t os = ostride;
+                asm volatile("" : "+l"(os));                      // opaque per pass: keeps ptxas from hoisting 60 output pointers out of the pass loop (onto the stack)
+                float* sp = part + (half ? ms : 0) * kTileM + row;
+                float* optr = outp + (half ? ms : 0) * os;        // where the filter held in a0 will be stored
+                float a0 = 0.f, a1 = 0.f;
+                auto emit = [&](float v) {              // v = complete mel power of the filter at optr
+                    if (valid) {
+                        *optr = (log10f(fmaxf(v, 1e-10f)) + 4.0f) / 4.0f;
+                        mx = fmaxf(mx, v);
+                        mn = fminf(mn, v);
+                    }
+                };
+                auto flush = [&]() {                    // the filter held in a0 is complete for this pass
+                    if (pass == 0) *sp = a0;
+                    else emit((*sp + a0) * sc2);
+                    sp += kTileM;
+                    optr += os;
+                    a0 = a1; a1 = 0.f;
+                };
+                int nshared = 0;
+                auto flush_hi = [&]() {                 // high half: its first two filters are the shared ones
+                    if (nshared < 2) {
+                        float* s2 = sh2 + nshared * kTileM;
+                        *s2 = pass == 0 ? a0 : *s2 + a0;
+                        ++nshared;
+                        sp += kTileM;
+                        optr += os;
+                        a0 = a1; a1 = 0.f;
+                    } else {
+                        flush();
+                    }
+                };
+                const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+                uint32_t c0[16], c1[16];
+                auto release_tmem = [&]() {             // this warp's share of TMEM is in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
+                };
+                // Straight-line code: the filterbank is a compile-time table (la_mel_table.inc), so the
+                // weights are FFMA immediates and the flush points are static. The first bin of each
+                // half never flushes (the accumulators start empty on that filter).
 #define LA_BIN(K, LO, W0, W1, NF)                                                                 \
-            {                                                                                     \
-                const float xr = __uint_as_float(re[(K) & 15]), xi = __uint_as_float(im[(K) & 15]); \
-                const float pw = xr * xr + xi * xi;                                               \
-                if ((NF) >= 1 && (K) != 0 && (K) != kSplit) flush();                              \
-                if ((NF) >= 2 && (K) != 0 && (K) != kSplit) flush();                              \
-                a0 = fmaf(W0, pw, a0);                                                            \
-                a1 = fmaf(W1, pw, a1);                                                            \
-            }
+                {                                                                                     \
+                    const float x = __uint_as_float(c0[(K) & 15]) + __uint_as_float(c1[(K) & 15]);    \
+                    const float pw = x * x;                                                           \
+                    if ((NF) >= 1 && (K) != 0 && (K) != kSplit) LA_FLUSH();                           \
+                    if ((NF) >= 2 && (K) != 0 && (K) != kSplit) LA_FLUSH();                           \
+                    a0 = fmaf(W0, pw, a0);                                                            \
+                    a1 = fmaf(W1, pw, a1);                                                            \
+                }
 #define LA_CHUNK(C, LAST)                                                                         \
-            {                                                                                     \
-                tmem_ld16(lane_base + 16 * (C), re);                                              \
-                tmem_ld16(lane_base + kNpad + 16 * (C), im);                                      \
-                tmem_ld_wait();                                                                   \
-                if (LAST) release_tmem();                                                         \
-                LA_MEL_CHUNK_##C(LA_BIN)                                                          \
-            }
-            if (p.dbg & 1) {
-                release_tmem();
-                continue;
-            }
-            if (!half) {
-                LA_CHUNK(0, false) LA_CHUNK(1, false) LA_CHUNK(2, false)
-                LA_CHUNK(3, false) LA_CHUNK(4, false) LA_CHUNK(5, true)
+                {                                                                                     \
+                    tmem_ld16(lane_base + 16 * (C), c0);                                              \
+                    tmem_ld16(lane_base + kNpad + 16 * (C), c1);                                      \
+                    tmem_ld_wait();                                                                   \
+                    if (LAST) release_tmem();                                                         \
+                    LA_MEL_CHUNK_##C(LA_BIN)                                                          \
+                }
+                if (!half) {
+#define LA_FLUSH flush
+                    LA_CHUNK(0, false) LA_CHUNK(1, false) LA_CHUNK(2, false)
+                    LA_CHUNK(3, false) LA_CHUNK(4, false) LA_CHUNK(5, true)
 #pragma unroll
-                for (int i = 0; i < LA_MEL_TAIL0; ++i) flush();
-            } else {
-                LA_CHUNK(6, false) LA_CHUNK(7, false) LA_CHUNK(8, false) LA_CHUNK(9, false)
-                LA_CHUNK(10, false) LA_CHUNK(11, false) LA_CHUNK(12, true)
+                    for (int i = 0; i < LA_MEL_TAIL0; ++i) flush();
+#undef LA_FLUSH
+                } else {
+#define LA_FLUSH flush_hi
+                    LA_CHUNK(6, false) LA_CHUNK(7, false) LA_CHUNK(8, false) LA_CHUNK(9, false)
+                    LA_CHUNK(10, false) LA_CHUNK(11, false) LA_CHUNK(12, true)
 #pragma unroll
-                for (int i = 0; i < LA_MEL_TAIL1; ++i) flush();
-            }
+                    for (int i = 0; i < LA_MEL_TAIL1; ++i) flush_hi();
+#undef LA_FLUSH
+                }
 #undef LA_CHUNK
 #undef LA_BIN
-            if ((warp == 4 || warp == 8) && lane == 0) trace(p.dbg, 2, tl, warp == 4 ? 3 : 6);
-            // Filters ms and ms + 1 are fed from both halves: the high half stores its partial
-            // sums like any other filter, the low half adds its own after the barrier.
-            named_bar_sync(3, 256);                     // both halves, one barrier instruction
-            if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 4);
-            if (!half && valid) {
-                float* o0 = outp + ms * ostride;
-                const float v0 = *o0 + a0, v1 = o0[ostride] + a1;
-                *o0 = v0;
-                o0[ostride] = v1;
-                mx = fmaxf(mx, fmaxf(v0, v1));
+                if (pass == 0) {
+                    if (!half) { r_ms0 = a0; r_ms1 = a1; }      // the low half's Re share of filters ms, ms + 1
+                } else {
+                    named_bar_sync(3, 256);                     // both halves: the high half's shares are in shared2
+                    if (!half) {
+                        optr = outp + ms * os;
+                        emit((sh2[0] + r_ms0 + a0) * sc2);
+                        optr += os;
+                        emit((sh2[kTileM] + r_ms1 + a1) * sc2);
+                    }
+                }
+                if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 2 * pass + 1);
             }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) atomicMax(p.group_max + c.group, __float_as_int(mx));   // mx >= 0: int order == float order
-            if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 1);
+            for (int o = 16; o; o >>= 1) {
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            }
+            if (lane == 0) {                            // powers are >= 0: int order == float order
+                atomicMax(p.group_max + c.group, __float_as_int(mx));
+                atomicMin(p.tile_min + tile, __float_as_int(mn));
+            }
         }
     }
 
@@ -518,85 +627,133 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
     }
 }
 
-// mel power -> log10(clamp 1e-10) -> max(x, gmax - 8) -> (x + 4) / 4 over the valid frames of every clip
-__global__ void logmel_finalize_kernel(const LogmelParams p) {
-    const ClipDesc c = p.clips[blockIdx.y];
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;       // one frame column per thread, coalesced along f
-    if (f >= c.n_frames) return;
+// max(x, gmax - 8) on the stored (x + 4) / 4 values; h(z) = (z + 4) / 4 is monotone, so
+// h(max(x, g)) == max(h(x), h(g)) bit for bit. One block per tile; tiles whose smallest mel power is
+// above the floor (almost all of them: the floor is 80 dB below the loudest cell) exit at once.
+__global__ void logmel_floor_kernel(const LogmelParams p) {
+    const int tile = blockIdx.x;
+    const ClipDesc c = p.clips[p.tile_clip[tile]];
     const float gmax = log10f(fmaxf(__int_as_float(p.group_max[c.group]), 1e-10f));
-    const float floor_v = gmax - 8.0f;
+    const float floor_y = ((gmax - 8.0f) + 4.0f) / 4.0f;
+    const float min_y = (log10f(fmaxf(__int_as_float(p.tile_min[tile]), 1e-10f)) + 4.0f) / 4.0f;
+    if (min_y >= floor_y) return;
+    const int f = (tile - c.tile0) * kTileM + threadIdx.x;     // one frame column per thread, coalesced along f
+    if (f >= c.n_frames) return;
     float* q = p.out + c.out_off + f;
 #pragma unroll 8
-    for (int m = 0; m < kMels; ++m, q += c.out_stride) {
-        const float x = log10f(fmaxf(*q, 1e-10f));
-        *q = (fmaxf(x, floor_v) + 4.0f) / 4.0f;
-    }
+    for (int m = 0; m < kMels; ++m, q += c.out_stride)
+        if (*q < floor_y) *q = floor_y;
 }
 
-__global__ void fill_int_kernel(int* p, int n, int v) {
+__global__ void logmel_init_kernel(int* group_max, int n_groups, int* tile_min, int n_tiles) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+    if (i < n_groups) group_max[i] = 0;                        // 0.0f: powers are >= 0
+    if (i < n_tiles) tile_min[i] = 0x7f800000;                 // +inf
 }
 
 // ---- host: constant tables ---------------------------------------------------------------
-static void tf32_split(double v, float* hi, float* lo) {
-    float f = (float)v;
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    u = (u + 0x1000u) & 0xffffe000u;          // round to nearest TF32 (10 explicit mantissa bits)
-    float h;
-    memcpy(&h, &u, 4);
-    *hi = h;
-    float l = (float)(v - (double)h);
-    memcpy(&u, &l, 4);
-    u = (u + 0x1000u) & 0xffffe000u;          // pre-round lo as well: operand truncation becomes a no-op
-    memcpy(&l, &u, 4);
-    *lo = l;
+static uint16_t f32_to_f16_rn(float f) {       // IEEE round-to-nearest-even, subnormals kept
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    uint32_t mant = x & 0x7fffffu;
+    const int exp = (int)((x >> 23) & 0xffu);
+    if (exp == 255) return (uint16_t)(sign | 0x7c00u | (mant ? 0x200u : 0u));
+    const int e = exp - 127 + 15;
+    if (e >= 31) return (uint16_t)(sign | 0x7c00u);
+    if (e <= 0) {
+        if (e < -10) return (uint16_t)sign;
+        mant |= 0x800000u;
+        const int shift = 14 - e;                                   // 14..24
+        uint32_t h = mant >> shift;
+        const uint32_t rem = mant & ((1u << shift) - 1u), half = 1u << (shift - 1);
+        if (rem > half || (rem == half && (h & 1u))) ++h;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((uint32_t)e << 10) | (mant >> 13);
+    const uint32_t rem = mant & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;         // a carry into the exponent is the right answer
+    return (uint16_t)(sign | h);
+}
+static double f16_to_f64(uint16_t h) {
+    const int e = (h >> 10) & 0x1f, m = h & 0x3ff;
+    double v;
+    if (e == 0) v = std::ldexp((double)m, -24);
+    else if (e == 31) v = m ? NAN : INFINITY;
+    else v = std::ldexp((double)(m | 0x400), e - 25);
+    return (h & 0x8000) ? -v : v;
+}
+
+// basis blocks [pass 2][k-step 13][slice 3], each [ki 2][ni 26][8 rows (bin)][8 fp16 (sample)] -- the UMMA
+// canonical K-major no-swizzle layout. Slices of U = 2^14 w[n] cos|(-sin)(2 pi k n / 400) (fp64):
+// B1 = 64 rint(U / 64), B2 = fp16(U - B1), B3 = fp16(U - B1 - B2).
+static void build_basis(std::vector<uint16_t>& h) {
+    h.assign((size_t)kIters * kSlices * (kBBytes / 2), 0);
+    const double PI = 3.14159265358979323846;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int ks = 0; ks < kKSteps; ++ks)
+            for (int kk = 0; kk < 16; ++kk) {
+                const int n = ks * 16 + kk;                                   // 0..207; rows 0 and 201.. are zero
+                if (n < 1 || n > kNfft / 2) continue;
+                const double w = 0.5 - 0.5 * std::cos(2.0 * PI * n / kNfft);
+                for (int b = 0; b < kBins; ++b) {
+                    const int ph = (int)(((long long)b * n) % kNfft);         // exact phase reduction
+                    double v;
+                    // n = 200 folds onto itself: the kernel forms e[200] = 2 x[200], so halve its row
+                    if (pass == 0) v = (n == kNfft / 2 ? 0.5 : 1.0) * w * std::cos(2.0 * PI * ph / kNfft);
+                    else v = (n == kNfft / 2) ? 0.0 : -w * std::sin(2.0 * PI * ph / kNfft);
+                    const double U = v * 16384.0;
+                    const double B1 = 64.0 * std::nearbyint(U / 64.0);
+                    const uint16_t h1 = f32_to_f16_rn((float)B1);
+                    const uint16_t h2 = f32_to_f16_rn((float)(U - B1));
+                    const uint16_t h3 = f32_to_f16_rn((float)(U - B1 - f16_to_f64(h2)));
+                    const size_t inner = (size_t)(kk >> 3) * (kBLbo / 2) + (size_t)(b >> 3) * 64 + (b & 7) * 8 + (kk & 7);
+                    const size_t base = (size_t)(pass * kKSteps + ks) * kSlices * (kBBytes / 2);
+                    h[base + inner] = h1;
+                    h[base + (kBBytes / 2) + inner] = h2;
+                    h[base + 2 * (kBBytes / 2) + inner] = h3;
+                }
+            }
 }
 
 struct LogmelTables {
     std::mutex mu;
-    float* d_basis[64] = {nullptr};
+    __half* d_basis[64] = {nullptr};
 };
 static LogmelTables g_tab;
 
-static cudaError_t ensure_tables(int device, const float** basis_out) {
+static cudaError_t ensure_tables(int device, const __half** basis_out) {
     std::lock_guard<std::mutex> lock(g_tab.mu);
     if (!g_tab.d_basis[device]) {
-        // basis blocks: per k-step j: [C_hi | C_lo] (even half-step) then [S_hi | S_lo] (odd), each
-        // matrix in the canonical K-major layout [ki 2][ni 26][8 rows (bin)][4 floats (sample)]
-        std::vector<float> h((size_t)kKSteps * 4 * (kBBytes / 4), 0.f);
-        const double PI = 3.14159265358979323846;
-        for (int j = 0; j < kKSteps; ++j)
-            for (int kk = 0; kk < 8; ++kk) {
-                const int n = j * 8 + kk + 1;                               // 1..200
-                const double w = 0.5 - 0.5 * std::cos(2.0 * PI * n / kNfft);
-                for (int b = 0; b < kNpad; ++b) {
-                    double cv = 0.0, sv = 0.0;
-                    if (b < kBins) {
-                        const int ph = (int)(((long long)b * n) % kNfft);     // exact phase reduction
-                        // n = 200 folds onto itself: the kernel forms e[200] = 2 x[200], so halve its row
-                        cv = (n == kNfft / 2 ? 0.5 : 1.0) * w * std::cos(2.0 * PI * ph / kNfft);
-                        sv = (n == kNfft / 2) ? 0.0 : -w * std::sin(2.0 * PI * ph / kNfft);
-                    }
-                    const size_t inner = (size_t)(kk >> 2) * (kBLbo / 4) + (size_t)(b >> 3) * 32 + (b & 7) * 4 + (kk & 3);
-                    const size_t base = (size_t)j * 4 * (kBBytes / 4);
-                    tf32_split(cv, &h[base + inner], &h[base + (kBBytes / 4) + inner]);
-                    tf32_split(sv, &h[base + 2 * (kBBytes / 4) + inner], &h[base + 3 * (kBBytes / 4) + inner]);
-                }
-            }
-        float* d = nullptr;
-        cudaError_t e = cudaMalloc(&d, h.size() * 4);
+        std::vector<uint16_t> h;
+        build_basis(h);
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, h.size() * 2);
         if (e != cudaSuccess) return e;
-        e = cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+        e = cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { cudaFree(d); return e; }
-        g_tab.d_basis[device] = d;
+        g_tab.d_basis[device] = static_cast<__half*>(d);
     }
     *basis_out = g_tab.d_basis[device];
     return cudaSuccess;
 }
+// la_shutdown(): the per-device basis tables are the only device memory K1 keeps between calls
+void logmel_release_tables() {
+    std::lock_guard<std::mutex> lock(g_tab.mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d)
+        if (g_tab.d_basis[d]) {
+            cudaSetDevice(d);
+            cudaFree(g_tab.d_basis[d]);
+            g_tab.d_basis[d] = nullptr;
+        }
+    cudaSetDevice(cur);
+}
 
-size_t logmel_smem_bytes() { return (size_t)kBStages * kBStageBytes + kRawBytes + 256; }
+size_t logmel_smem_bytes() {
+    return (size_t)kBStages * kBStageBytes + kRawBytes + kPartBytes + kSharedBytes + kMiscBytes + 256;
+}
 
 }  // namespace la
 
@@ -627,24 +784,23 @@ static int logmel_run_impl(const float* d_wave, float* d_out, const std::vector<
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "cudaGetDevice: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
-    const float* basis = nullptr;
+    const __half* basis = nullptr;
     e = ensure_tables(device, &basis);
     if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "tables: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
     std::vector<ClipDesc> clips = clips_in;
     std::vector<int32_t> tile_clip;
-    int max_frames = 0;
     for (size_t ci = 0; ci < clips.size(); ++ci) {
         clips[ci].tile0 = (int32_t)tile_clip.size();
         const int nt = (clips[ci].n_frames + kTileM - 1) / kTileM;
         for (int t = 0; t < nt; ++t) tile_clip.push_back((int32_t)ci);
-        max_frames = std::max(max_frames, clips[ci].n_frames);
     }
     const int n_tiles = (int)tile_clip.size();
     if (n_tiles == 0) return LA_OK;
     const size_t o_clips = 0;
     const size_t o_tiles = lm_align(o_clips + clips.size() * sizeof(ClipDesc), 256);
     const size_t o_max = lm_align(o_tiles + tile_clip.size() * 4, 256);
-    const size_t need = o_max + lm_align((size_t)n_groups * 4, 256);
+    const size_t o_min = o_max + lm_align((size_t)n_groups * 4, 256);
+    const size_t need = o_min + lm_align((size_t)n_tiles * 4, 256);
     if (ws_bytes < need) { snprintf(g_lm_err, sizeof g_lm_err, "workspace too small"); LM_FAIL(LA_ERR_ARG); }
     unsigned char* ws = static_cast<unsigned char*>(d_ws);
     e = cudaMemcpyAsync(ws + o_clips, clips.data(), clips.size() * sizeof(ClipDesc), cudaMemcpyHostToDevice, stream);
@@ -658,8 +814,9 @@ static int logmel_run_impl(const float* d_wave, float* d_out, const std::vector<
     p.n_tiles = n_tiles; p.n_clips = (int)clips.size();
     p.basis = basis;
     p.group_max = reinterpret_cast<int*>(ws + o_max);
+    p.tile_min = reinterpret_cast<int*>(ws + o_min);
     { const char* d = getenv("LA_LOGMEL_DBG"); p.dbg = d ? atoi(d) : 0; }
-    fill_int_kernel<<<(n_groups + 255) / 256, 256, 0, stream>>>(p.group_max, n_groups, 0);   // 0.0f: powers are >= 0
+    logmel_init_kernel<<<(std::max(n_groups, n_tiles) + 255) / 256, 256, 0, stream>>>(p.group_max, n_groups, p.tile_min, n_tiles);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const size_t smem = logmel_smem_bytes();
@@ -667,12 +824,7 @@ static int logmel_run_impl(const float* d_wave, float* d_out, const std::vector<
     if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "smem attr: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
     const int ctas = la::g_logmel_ctas > 0 ? std::min(la::g_logmel_ctas, sms) : sms;
     logmel_kernel<<<std::min(n_tiles, ctas), kLogmelThreads, smem, stream>>>(p);
-    for (size_t c0 = 0; c0 < clips.size(); c0 += 65535) {            // gridDim.y limit
-        LogmelParams q = p;
-        q.clips = p.clips + c0;
-        const unsigned ny = (unsigned)std::min<size_t>(65535, clips.size() - c0);
-        logmel_finalize_kernel<<<dim3((max_frames + 127) / 128, ny), 128, 0, stream>>>(q);
-    }
+    logmel_floor_kernel<<<n_tiles, kTileM, 0, stream>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "launch: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
     return LA_OK;
@@ -685,10 +837,18 @@ int la_debug_logmel_trace(unsigned long long* h_out) {
     return cudaMemcpyFromSymbol(h_out, la::g_trace, sizeof(unsigned long long) * 4 * 8 * 32) == cudaSuccess ? 0 : -2;
 }
 
+// test hook (not in the public header): the host-built fp16 basis table, so a CPU test can check the slicing
+size_t la_debug_logmel_basis(uint16_t* out, size_t cap_elems) {
+    std::vector<uint16_t> h;
+    la::build_basis(h);
+    if (out) memcpy(out, h.data(), std::min(cap_elems, h.size()) * 2);
+    return h.size();
+}
+
 size_t la_logmel_workspace_bytes(int n_clips, int64_t total_samples) {
     if (n_clips < 0 || total_samples < 0) return 0;
     const size_t tiles = (size_t)(total_samples / la::kHop) / la::kTileM + (size_t)n_clips + 1;
-    return lm_align((size_t)n_clips * sizeof(la::ClipDesc), 256) + lm_align(tiles * 4, 256) +
+    return lm_align((size_t)n_clips * sizeof(la::ClipDesc), 256) + 2 * lm_align(tiles * 4, 256) +
            lm_align((size_t)std::max(n_clips, 1) * 4, 256) + 256;
 }
 
