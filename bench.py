@@ -5,19 +5,30 @@
 
 Workload (BASELINE.json configs[1]): an Opencpop-test-shaped batch of 2,000 synthetic clips of
 5-15 s, head width V = 21129 (fp32 logits, 84.5 KB per 20 ms frame), CTC-flavour decode
-(perform_viterbi_ctc) against 2.4 char/s pinyin-class lyrics. One "step" = one pass of the hot
-path (K1 tcgen05 log-mel of every clip's waveform, K2 fused log-softmax + gather over the head
-logits, K3 Viterbi + backtrace) over the whole batch. The Whisper encoder + GRU head between K1
-and K2 are stock PyTorch and outside the product, so the logits are synthetic and resident.
+(perform_viterbi_ctc) against 2.4 char/s pinyin-class lyrics. The Whisper encoder + GRU head between
+K1 and K2 are stock PyTorch and outside the product, so the logits are synthetic and resident.
 
-  value  : whole-job audio-s/s with the logits resident in HBM (84.5 GB per GPU, >> L2, so every
-           step streams from HBM); CUDA-event timed, max over ranks.
-  e2e    : the same metric through the reference-facing call `perform_viterbi_ctc(cpu_tensor,
-           labels)`, batch size 1 as in inference_alignment.py, logits in PINNED HOST memory --
-           H2D copy of every clip's logits and D2H of its alignment inside the timed region.
-  roofline / cpu_baseline : see DESIGN.md ("Measurement").
-With N > 1 (torchrun) every rank owns its own 2,000 clips (weak scaling) and the step ends with
-the NCCL gather of all alignments to rank 0.
+One "step" = one pass of the WHOLE hot path over the batch, as SURVEY.md 8(d) defines it -- from
+"waveforms and logits resident on the device" to "on/offset int32 on the host":
+    K1 tcgen05 log-mel of every clip's waveform
+ -> label flattening + la_plan_create (the replacement of the reference's per-utterance label strip and
+    dp/bt allocation, utils/alignment.py:141-152) -- host work, INSIDE the timed region
+ -> K2 fused log-softmax + gather over the head logits -> K3 Viterbi + backtrace
+ -> D2H of first / last+1 / score / status -> numpy int32 on the host (and, at N > 1, the NCCL gather).
+
+  value    : whole-job audio-s/s of that step; CUDA-event timed around the K steps, max over ranks.
+  kernels  : the same three kernels timed alone (pre-built plan, nothing but launches), for reference.
+  roofline : K2, the dominant kernel: algorithmic bytes / its CUDA-event time inside the timed steps.
+  e2e      : the same metric through the REFERENCE-SHAPED call with HOST buffers, one clip per call as
+             inference_alignment.py does (default --batch-size 1): log_mel_spectrogram(pinned waveform) +
+             perform_viterbi_ctc(pinned cpu logits[1,T,V], labels) -> nested Python lists. H2D of every
+             clip's logits and D2H of its alignment are inside the timed region. Two more legs are
+             reported beside it: the repo's ragged batch API from host buffers, and the one-line-edit
+             drop-in where the caller keeps the logits on the GPU (perform_viterbi_ctc(cuda logits)).
+  cpu_baseline / --impl reference : the UNMODIFIED reference decode (utils/alignment.py, vendored to the
+             git-ignored oracle/_ref/ by __graft_entry__.build()) + whisper's torch.stft log-mel, on the
+             box's host cores, on a bounded sample of the same workload.
+With N > 1 (torchrun) every rank owns its own 2,000 clips (weak scaling).
 """
 from __future__ import annotations
 
@@ -37,8 +48,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_CLIPS = 2000
-POOL_CLIPS = 100          # pinned host pool for the e2e leg (~4.2 GB), recycled 20x per step
-CPU_SAMPLE_CLIPS = 16
+POOL_CLIPS = 100          # pinned host pool for the e2e legs (~4.2 GB), recycled 20x per step
+CPU_SAMPLE_CLIPS = 64     # cpu_baseline leg: first 64 clips, 5 passes
+REF_STEP_CLIPS = 32       # --impl reference: clips per step
 
 
 def measured_peaks():
@@ -100,9 +112,10 @@ class ClockSampler:
 # CPU arm: the reference's own decode on the host cores
 # ----------------------------------------------------------------------------------------------
 def cpu_decode_fn():
-    """Returns (fn(pred_cpu[1,T,V] tensor, labels) -> onoff, kind). The unmodified reference when
-    its tree is mounted (dev container), else the oracle port: the reference's torch CPU emission
-    chain (all intra-op threads, as shipped) + the C restatement of its DP."""
+    """Returns (fn(pred_cpu[1,T,V] tensor, labels) -> onoff, kind). The unmodified reference
+    (utils/alignment.py, from /root/reference or the vendored oracle/_ref/) when it can be imported;
+    else the oracle port: the reference's torch CPU emission chain (all intra-op threads, as shipped) +
+    the C restatement of its DP."""
     from oracle import ref_shim
     if ref_shim.available():
         ref = ref_shim.load()
@@ -162,10 +175,6 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--k1-sms", type=int, default=0,
-                    help="SMs given to K1 while it runs concurrently with K2/K3 on a second stream (0 = run K1, K2, K3 back "
-                         "to back, the default: measured 15.8 ms back to back vs 18.6-22.7 ms concurrent with 20-36 SMs for "
-                         "K1 -- K1's basis loads and K2's stream fight over L2/HBM)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -185,6 +194,7 @@ def main():
 
     t_begin = time.perf_counter()
     import torch.distributed as dist
+    import lyricalignment_b200 as la
     from lyricalignment_b200 import _lib, alignment as A, audio as LA, sharded
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -198,94 +208,41 @@ def main():
     V = synth.V_HEAD
     total_T = int(batch.t_len.sum())
     logits = synth.planted_logits(batch, V, ctc=True, device=dev, seed=114514 + rank)
-    l_len, cols = A._resolve_columns(batch.labels, V - 2)
-    plan = A.AlignPlan(A.MODE_CTC, V, batch.t_len, l_len, cols, local_rank)
-    ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
-    first = torch.empty(plan.total_labels, dtype=torch.int32, device=dev)
-    last = torch.empty(plan.total_labels, dtype=torch.int32, device=dev)
-    score = torch.empty(plan.n_utt, dtype=torch.float64, device=dev)
-    status = torch.empty(plan.n_utt, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
     # K1 inputs/outputs: ragged waveforms -> per-clip [80][F] log-mel (each clip its own call/max)
     wave, w_off = synth.synthetic_waveforms(batch, device=dev, seed=114514 + rank)
     n_samp = batch.n_samples.astype(np.int32)
     mel_frames = (n_samp // 160).astype(np.int32)
     mel_off = np.concatenate([[0], np.cumsum(80 * mel_frames.astype(np.int64))[:-1]]).astype(np.int64)
     mel_out = torch.empty(int(80 * mel_frames.astype(np.int64).sum()), dtype=torch.float32, device=dev)
-    mel_ws = torch.empty(int(lib.la_logmel_workspace_bytes(len(n_samp), int(n_samp.astype(np.int64).sum()))),
-                         dtype=torch.uint8, device=dev)
 
-    # K1 works on the waveforms, K2/K3 on the head logits (the stock encoder sits between them), so inside
-    # one pass over the batch they are independent: K1 runs on a side stream on its own SM partition.
-    overlap = args.k1_sms > 0
-    sms_total = torch.cuda.get_device_properties(dev).multi_processor_count
-    if overlap:
-        lib.la_set_sm_budget(args.k1_sms, sms_total - args.k1_sms)
-        side = torch.cuda.Stream(device=dev)
-        ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
-        ev_k1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + args.warmup)]
-    step_no = [0]
+    launches = [0]
 
-    def step(ev_m=None, ev_a=None, ev_b=None):
-        if ev_m is not None:
-            ev_m.record()
-        if overlap:
-            ev_fork.record()
-            side.wait_event(ev_fork)
-            with torch.cuda.stream(side):
-                k1a, k1b = ev_k1[step_no[0] % len(ev_k1)]
-                k1a.record()
-                _lib.check(lib.la_logmel_ragged(wave.data_ptr(), len(n_samp), w_off.ctypes.data, n_samp.ctypes.data,
-                                                mel_out.data_ptr(), mel_off.ctypes.data, mel_frames.ctypes.data,
-                                                mel_ws.data_ptr(), side.cuda_stream), "la_logmel_ragged")
-                k1b.record()
-                ev_join.record()
-            step_no[0] += 1
-        else:
-            _lib.check(lib.la_logmel_ragged(wave.data_ptr(), len(n_samp), w_off.ctypes.data, n_samp.ctypes.data,
-                                            mel_out.data_ptr(), mel_off.ctypes.data, mel_frames.ctypes.data,
-                                            mel_ws.data_ptr(), stream), "la_logmel_ragged")
-        if ev_a is not None:
-            ev_a.record()
-        _lib.check(lib.la_emit(plan.handle, logits.data_ptr(), V, None, 0, ws.data_ptr(), stream), "la_emit")
-        if ev_b is not None:
-            ev_b.record()
-        _lib.check(lib.la_viterbi(plan.handle, ws.data_ptr(), first.data_ptr(), last.data_ptr(),
-                                  score.data_ptr(), status.data_ptr(), stream), "la_viterbi")
+    def step(ev=None):
+        """The whole hot path through the public API, device-resident inputs -> int32 results on the host."""
+        if ev:
+            ev[0].record()
+        LA.log_mel_spectrogram_ragged(wave, w_off, n_samp, out=mel_out, out_offsets=mel_off, out_strides=mel_frames)   # K1
+        if ev:
+            ev[1].record()
+        job = A.align_clips_async(logits, batch.t_len, batch.labels, timing=(ev[2], ev[3]) if ev else None)   # labels + plan + K2 + K3 + D2H
+        launches[0] = 3 + job.plan.num_launches        # K1: init + logmel + floor; K2; one K3 launch per bucket
+        res = job.result()                              # first / last+1 int32, score, status: numpy on the host
         if world > 1:
-            res = A.AlignResult(first, last, score, status, l_len)
-            gather_device(res, dev, dist)
-        if overlap:
-            torch.cuda.current_stream(dev).wait_event(ev_join)
-
-    # NCCL gather of the alignments to rank 0. Ranks own different clips, so their payloads differ in
-    # length: every rank sends a buffer padded to the common maximum (sizes exchanged once, at set-up).
-    n_payload = 2 * plan.total_labels + 3 * plan.n_utt
-    if world > 1:
-        mx = torch.tensor([n_payload], dtype=torch.int64, device=dev)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        n_payload_max = int(mx.item())
-        payload = torch.zeros(n_payload_max, dtype=torch.int32, device=dev)
-        gathered = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
-
-    def gather_device(res, dev, dist):
-        L, U = plan.total_labels, plan.n_utt
-        payload[0:L] = res.first
-        payload[L:2 * L] = res.last_plus1
-        payload[2 * L:2 * L + U] = res.status
-        payload[2 * L + U:2 * L + 3 * U] = res.score.view(torch.int32)
-        dist.gather(payload, gathered, dst=0)
+            sharded.gather_alignments(res, device=dev)  # NCCL: every rank's alignments to rank 0
+        return res
 
     def note(msg):
         if rank == 0:
             print(f"[bench +{time.perf_counter() - t_begin:6.1f}s] {msg}", file=sys.stderr, flush=True)
     note("inputs ready, warm-up")
     for _ in range(args.warmup):
-        step()
+        res = step()
     torch.cuda.synchronize()
-    assert int(status.max().item()) == 0, "synthetic clips must all be feasible"
+    assert int(res.status.max()) == 0, "synthetic clips must all be feasible"
+    l_len = res.l_len.astype(np.int64)
+    n_labels = int(l_len.sum())
 
-    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
@@ -295,20 +252,16 @@ def main():
         clocks.start()
     t_start.record()
     for k in range(args.steps):
-        step(*ev[k])
+        step(ev[k])
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clk = clocks.stop() if rank == 0 else None
-    lib.la_set_sm_budget(0, 0)                      # the e2e legs below run K1 and K2 back to back on the whole chip
-    note("device-resident timing done")
+    note("timed region done")
     ms_total = t_start.elapsed_time(t_end)
-    if overlap:
-        mel_ms = statistics.mean(a.elapsed_time(b) for a, b in ev_k1[-args.steps:]) if args.steps <= len(ev_k1) else float("nan")
-    else:
-        mel_ms = statistics.mean(m.elapsed_time(a) for m, a, b in ev)
-    emit_ms = statistics.mean(a.elapsed_time(b) for m, a, b in ev)
+    mel_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
+    emit_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in ev)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -317,10 +270,43 @@ def main():
     if world > 1:
         dist.all_reduce(audio_s, op=dist.ReduceOp.SUM)
     value = float(audio_s.item()) * args.steps / (ms_total / 1e3)
+    step_ms = ms_total / args.steps
 
-    # ---- roofline of the dominant kernel (K2) ----------------------------------------------
+    # ---- the three kernels alone (pre-built plan, launches only): explains `value`, is not `value` ----
+    lens, cols = A._resolve_columns(A._flatten_labels(batch.labels), V - 2)
+    plan = A.AlignPlan(A.MODE_CTC, V, batch.t_len, lens, cols, local_rank)
+    ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
+    first = torch.empty(plan.total_labels, dtype=torch.int32, device=dev)
+    last = torch.empty_like(first)
+    score = torch.empty(plan.n_utt, dtype=torch.float64, device=dev)
+    status = torch.empty(plan.n_utt, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    mel_ws = torch.empty(int(lib.la_logmel_workspace_bytes(len(n_samp), int(n_samp.astype(np.int64).sum()))),
+                         dtype=torch.uint8, device=dev)
+    kev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(5)]
+    for k in range(-2, 5):
+        e = kev[max(k, 0)]
+        e[0].record()
+        _lib.check(lib.la_logmel_ragged(wave.data_ptr(), len(n_samp), w_off.ctypes.data, n_samp.ctypes.data,
+                                        mel_out.data_ptr(), mel_off.ctypes.data, mel_frames.ctypes.data,
+                                        mel_ws.data_ptr(), stream), "la_logmel_ragged")
+        e[1].record()
+        _lib.check(lib.la_emit(plan.handle, logits.data_ptr(), V, None, 0, ws.data_ptr(), stream), "la_emit")
+        e[2].record()
+        _lib.check(lib.la_viterbi(plan.handle, ws.data_ptr(), first.data_ptr(), last.data_ptr(),
+                                  score.data_ptr(), status.data_ptr(), stream), "la_viterbi")
+        e[3].record()
+    torch.cuda.synchronize()
+    k1_alone = statistics.mean(e[0].elapsed_time(e[1]) for e in kev)
+    k2_alone = statistics.mean(e[1].elapsed_time(e[2]) for e in kev)
+    k3_alone = statistics.mean(e[2].elapsed_time(e[3]) for e in kev)
+    plan.close()
+
+    # ---- roofline of the dominant kernel (K2), from the events inside the timed steps -------------
     peak, peak_src = measured_peaks()
-    algo_bytes = 4.0 * total_T * V + 4.0 * float(np.sum(batch.t_len.astype(np.int64) * (l_len + 1)))
+    tl64 = batch.t_len.astype(np.int64)
+    emis_bytes = 4.0 * float(np.sum(tl64 * (l_len + 1)))
+    algo_bytes = 4.0 * total_T * V + emis_bytes
     achieved = algo_bytes / (emit_ms / 1e3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "k2_traffic.json")
@@ -333,19 +319,25 @@ def main():
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": round(emit_ms, 4)}
-    # secondary kernels, for the record (DESIGN.md "Measurement")
-    mel_flops = 3 * 2 * 2.0 * 200 * 208 * float(np.sum((mel_frames + 127) // 128 * 128))   # 3xTF32, Re+Im, padded tiles
-    mel_bytes = 4.0 * float(n_samp.astype(np.int64).sum()) + 2 * 4.0 * 80 * float(mel_frames.astype(np.int64).sum())
-    step_ms = ms_total / args.steps
-    kernels = {"k1_logmel_ms": round(mel_ms, 4), "k1_tf32_tflops": round(mel_flops / (mel_ms / 1e3) / 1e12, 1),
-               "k1_algorithmic_gbs": round(mel_bytes / (mel_ms / 1e3) / 1e9, 1),
-               "k2_emit_ms": round(emit_ms, 4),
-               "k3_viterbi_and_rest_ms": round(step_ms - emit_ms - (0.0 if overlap else mel_ms), 4),
-               "k1_concurrent_with_k2": bool(overlap), "k1_sms": args.k1_sms if overlap else sms_total,
-               # K3 is latency-bound (a frame step is a dependent chain): its nominal HBM figure, for the record
-               "k3_algorithmic_gbs": round((2 * 4.0 * float(np.sum(batch.t_len.astype(np.int64) * (l_len + 1))) +
-                                            8.0 * float(np.sum(batch.t_len.astype(np.int64) * ((l_len + 32) // 32 * 32) // 8)))
-                                           / max(step_ms - emit_ms - (0.0 if overlap else mel_ms), 1e-6) / 1e6, 1)}
+    # K1: tensor-nominal. 6 fp16 MMAs x 13 k-steps x 2 passes per 128-frame tile, M128 N208 K16.
+    tiles = float(np.sum((mel_frames + 127) // 128))
+    mel_flops = 2.0 * 128 * 208 * 16 * 6 * 26 * tiles
+    mel_bytes = 4.0 * float(n_samp.astype(np.int64).sum()) + 4.0 * 80 * float(mel_frames.astype(np.int64).sum())
+    # K3: 4 T (L+1) emissions read + ceil(S/4) T backpointer bytes written + read back + 8 L out.
+    k3_bytes = emis_bytes + 2.0 * float(np.sum(tl64 * ((2 * l_len + 1 + 3) // 4))) + 8.0 * n_labels
+    kernels = {"k1_logmel_ms": round(mel_ms, 4), "k2_emit_ms": round(emit_ms, 4),
+               "host_plan_k3_d2h_ms": round(step_ms - mel_ms - emit_ms, 4),
+               "alone": {"k1_logmel_ms": round(k1_alone, 4), "k2_emit_ms": round(k2_alone, 4),
+                         "k3_viterbi_ms": round(k3_alone, 4),
+                         "sum_ms": round(k1_alone + k2_alone + k3_alone, 4),
+                         "audio_s_per_s": round(batch.audio_seconds / ((k1_alone + k2_alone + k3_alone) / 1e3), 1)},
+               "host_and_copy_share_of_step": round(max(0.0, 1.0 - (k1_alone + k2_alone + k3_alone) / step_ms), 4),
+               "k1_f16_tflops": round(mel_flops / (k1_alone / 1e3) / 1e12, 1),
+               "k1_algorithmic_gbs": round(mel_bytes / (k1_alone / 1e3) / 1e9, 1),
+               "k3_algorithmic_bytes": k3_bytes,
+               "k3_algorithmic_gbs": round(k3_bytes / (k3_alone / 1e3) / 1e9, 1),
+               "k3_frac_of_hbm_peak": round(k3_bytes / (k3_alone / 1e3) / 1e9 / peak, 4),
+               "k3_note": "latency-bound dependent chain (one fp64 add per frame on the critical path), not a streaming kernel"}
 
     # ---- e2e + cpu baseline on rank 0's pinned pool ----------------------------------------
     e2e, cpu = None, None
@@ -357,9 +349,10 @@ def main():
         torch.cuda.synchronize()
         offs = np.concatenate([[0], np.cumsum(batch.t_len[:pool_n])])
         pool_pred = [host[offs[i]:offs[i + 1]].unsqueeze(0) for i in range(pool_n)]
-        import lyricalignment_b200 as la
+        pool_pred_dev = [logits[offs[i]:offs[i + 1]].unsqueeze(0) for i in range(pool_n)]
         n_calls = args.clips
         lab_sets = [synth.opencpop_shaped(pool_n, seed=7000 + 31 * rank + j).labels for j in range((n_calls + pool_n - 1) // pool_n)]
+
         # labels drawn for other durations may be too long for this clip: keep them feasible
         def lab_for(i):
             lab = lab_sets[i // pool_n][i % pool_n]
@@ -367,65 +360,82 @@ def main():
 
         wave_host = wave.cpu().pin_memory()
         pool_wave = [wave_host[w_off[i]:w_off[i] + int(n_samp[i])] for i in range(pool_n)]
+        pool_wave_end = int(w_off[pool_n - 1] + n_samp[pool_n - 1])
 
-        # (a) headline: the ragged public API, one call per 100-clip batch, HOST buffers in and out
-        def e2e_step():
-            tot = 0
-            for b0 in range(0, n_calls, pool_n):
-                nb = min(pool_n, n_calls - b0)
-                mel, _, _ = LA.log_mel_spectrogram_ragged(wave_host[:pool_wave_end], w_off[:nb], n_samp[:nb])
-                res = la.align_clips(host[:int(offs[nb])], batch.t_len[:nb], [lab_for(b0 + i) for i in range(nb)],
-                                     staging_bytes=int(os.environ.get("BENCH_STAGING_MB", "0")) << 20)
-                tot += sum(len(u) for u in la.onoff_seconds(res))
-            return tot
-
-        # (b) the literal drop-in loop of inference_alignment.py (default --batch-size 1)
+        # (a) HEADLINE e2e: the literal drop-in loop of inference_alignment.py (default --batch-size 1)
         def dropin_step():
             tot = 0
             for i in range(n_calls):
                 j = i % pool_n
-                mel = LA.log_mel_spectrogram(pool_wave[j])                 # B1: host waveform -> device log-mel
-                out = la.perform_viterbi_ctc(pool_pred[j], [lab_for(i).tolist()])   # B2: host logits -> on/offsets
+                LA.log_mel_spectrogram(pool_wave[j])                               # B1: host waveform -> device log-mel
+                out = la.perform_viterbi_ctc(pool_pred[j], [lab_for(i).tolist()])   # B2: host logits -> on/offsets (lists)
                 tot += len(out[0])
             return tot
-        pool_wave_end = int(w_off[pool_n - 1] + n_samp[pool_n - 1])
+
+        # (b) the repo's ragged batch API, one call per 100-clip batch, HOST buffers in and out
+        def ragged_step():
+            tot = 0
+            for b0 in range(0, n_calls, pool_n):
+                nb = min(pool_n, n_calls - b0)
+                LA.log_mel_spectrogram_ragged(wave_host[:pool_wave_end], w_off[:nb], n_samp[:nb])
+                r = la.align_clips(host[:int(offs[nb])], batch.t_len[:nb], [lab_for(b0 + i) for i in range(nb)],
+                                   staging_bytes=int(os.environ.get("BENCH_STAGING_MB", "0")) << 20)
+                tot += sum(len(u) for u in la.onoff_seconds(r))
+            return tot
+
+        # (c) the one-line-edit drop-in: the caller drops its `.cpu()` (inference_alignment.py:161), logits stay on the GPU
+        def cuda_dropin_step():
+            tot = 0
+            for i in range(n_calls):
+                j = i % pool_n
+                LA.log_mel_spectrogram(pool_wave[j])
+                out = la.perform_viterbi_ctc(pool_pred_dev[j], [lab_for(i).tolist()])
+                tot += len(out[0])
+            return tot
+
         note("e2e warm-up")
-        e2e_step()
-        dropin_step()
+        dropin_step(); ragged_step(); cuda_dropin_step()
+
+        def timed(fn, reps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                n = fn()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt.item()) / reps, n
         note("e2e timing")
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            n_lab = e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        dropin_step()
-        torch.cuda.synchronize()
-        dt_dropin = time.perf_counter() - t0
-        tt = torch.tensor([dt, dt_dropin], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt_dropin, n_lab = timed(dropin_step, args.e2e_steps)
+        dt_ragged, _ = timed(ragged_step, 1)
+        dt_cuda, _ = timed(cuda_dropin_step, 1)
         e2e_audio = float(sum(batch.durations[i % pool_n] for i in range(n_calls))) * world
-        h2d = float(sum(int(batch.t_len[i % pool_n]) for i in range(n_calls))) * V * 4 + \
-            4.0 * float(sum(int(n_samp[i % pool_n]) for i in range(n_calls)))
-        e2e = {"value": round(e2e_audio * args.e2e_steps / float(tt[0].item()), 1), "unit": "audio-s/s",
-               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": float(n_lab * 8 + n_calls * 12) * world,
-               "steps": args.e2e_steps,
-               "call": f"per {pool_n}-clip batch: audio.log_mel_spectrogram_ragged(pinned waveforms) + "
-                       "align_clips(pinned cpu logits[sumT,V], t_len, labels) -> onoff_seconds()",
-               "per_clip_dropin": {"value": round(e2e_audio / float(tt[1].item()), 1), "unit": "audio-s/s",
-                                   "call": "per clip, as inference_alignment.py with --batch-size 1: "
-                                           "audio.log_mel_spectrogram(pinned waveform) + "
-                                           "perform_viterbi_ctc(pinned cpu logits[1,T,V], labels)"}}
+        wave_bytes = 4.0 * float(sum(int(n_samp[i % pool_n]) for i in range(n_calls)))
+        h2d = float(sum(int(batch.t_len[i % pool_n]) for i in range(n_calls))) * V * 4 + wave_bytes
+        d2h = float(n_lab * 8 + n_calls * 12)
+        e2e = {"value": round(e2e_audio / dt_dropin, 1), "unit": "audio-s/s",
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": args.e2e_steps,
+               "call": "per clip, as inference_alignment.py with --batch-size 1: audio.log_mel_spectrogram(pinned "
+                       "waveform) + perform_viterbi_ctc(pinned cpu logits[1,T,V], labels) -> nested Python lists",
+               "limiter": f"PCIe: {h2d / 1e9:.1f} GB of fp32 logits per step per GPU at {h2d / dt_dropin / 1e9:.1f} GB/s",
+               "ragged_api": {"value": round(e2e_audio / dt_ragged, 1), "unit": "audio-s/s",
+                              "call": f"repo-only API, per {pool_n}-clip batch: audio.log_mel_spectrogram_ragged(pinned waveforms)"
+                                      " + align_clips(pinned cpu logits[sumT,V], t_len, labels) -> onoff_seconds()",
+                              "h2d_bytes_per_step": h2d * world},
+               "cuda_logits_dropin": {"value": round(e2e_audio / dt_cuda, 1), "unit": "audio-s/s",
+                                      "call": "per clip, entry script with its `.cpu()` dropped: log_mel_spectrogram(pinned "
+                                              "waveform) + perform_viterbi_ctc(CUDA logits[1,T,V], labels) -> nested Python lists",
+                                      "h2d_bytes_per_step": wave_bytes * world}}
         if rank == 0 and world == 1 and not args.skip_cpu:
+            note("cpu baseline")
             n_cpu = min(CPU_SAMPLE_CLIPS, pool_n)
-            v, kind, secs = time_cpu(pool_pred, batch.labels, batch.durations, n_cpu, 3, pool_wave)
+            v, kind, secs = time_cpu(pool_pred, batch.labels, batch.durations, n_cpu, 5, pool_wave)
             cpu = {"value": round(v, 1), "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": kind,
-                   "sample": f"first {n_cpu} clips of the workload ({sum(batch.durations[:n_cpu]):.0f} audio-s), "
-                             f"median of 3 passes, {secs:.2f} s per pass, host cpu_count={os.cpu_count()}"}
+                   "sample": f"first {n_cpu} clips of the workload ({sum(batch.durations[:n_cpu]):.0f} audio-s), same logits "
+                             f"(host copies), median of 5 passes, {secs:.2f} s per pass, host cpu_count={os.cpu_count()}"}
 
     note("done")
     faulthandler.cancel_dump_traceback_later()
@@ -433,19 +443,19 @@ def main():
         line = {
             "metric": "aligned audio-sec/sec (alignment decode path)", "value": round(value, 1), "unit": "audio-s/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 emissions / f64 DP", "data": "synthetic",
+            "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 emissions / f64 DP (K1: fp16 operand slices, f32 accumulate)", "data": "synthetic",
             "config": {"workload": f"configs[1]: Opencpop-test-shaped batch, {args.clips} clips of 5-15 s per GPU, "
-                                   f"V=21129 CTC decode, {plan.total_labels} syllables, {total_T} frames",
+                                   f"V=21129 CTC decode, {n_labels} syllables, {total_T} frames",
+                       "timed_region": "K1 -> label flattening + la_plan_create -> K2 -> K3 -> D2H -> int32 numpy on the host"
+                                       + (" -> NCCL gather to rank 0" if world > 1 else "") + " (public API: "
+                                       "log_mel_spectrogram_ragged + align_clips_async().result())",
                        "l2_policy": f"inputs larger than L2 ({4.0 * total_T * V / 1e9:.1f} GB of logits resident in HBM per GPU)",
-                       "parallelism": f"utterance-sharded x{world}" + (", NCCL gather of alignments in the step" if world > 1 else ""),
-                       "streams": (f"K1 on a side stream on {args.k1_sms} SMs, concurrent with K2/K3 on the other {sms_total - args.k1_sms}"
-                                   if overlap else "K1, K2, K3 back to back on one stream")},
+                       "parallelism": f"utterance-sharded x{world}" + (", NCCL gather of alignments in the step" if world > 1 else "")},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": (plan.num_launches + 3) * args.steps, "clocks": clk,
+            "gpu_launches": launches[0] * args.steps, "clocks": clk,
         }
         print(json.dumps(line))
-    plan.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -454,7 +464,7 @@ def run_reference_arm(args, synth):
     """--impl reference: the reference's CPU decode on the host cores, bounded sample per step."""
     torch.manual_seed(0)
     torch.set_num_threads(host_threads())
-    n = CPU_SAMPLE_CLIPS
+    n = REF_STEP_CLIPS
     batch = synth.opencpop_shaped(args.clips, seed=114514)
     sub = synth.ClipBatch(batch.durations[:n], batch.n_samples[:n], batch.t_len[:n], batch.labels[:n])
     pred = synth.planted_logits(sub, synth.V_HEAD, ctc=True, device="cpu", seed=114514)
@@ -477,8 +487,8 @@ def run_reference_arm(args, synth):
         step()
     dt = time.perf_counter() - t0
     value = sub.audio_seconds * args.steps / dt
-    sample = (f"each step = first {n} clips of the workload ({sub.audio_seconds:.0f} audio-s); "
-              f"host cpu_count={os.cpu_count()}")
+    sample = (f"each step = first {n} clips of the workload ({sub.audio_seconds:.0f} audio-s), one "
+              f"perform_viterbi_ctc call per clip as inference_alignment.py does; host cpu_count={os.cpu_count()}")
     cpu = {"value": round(value, 1), "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample}
     print(json.dumps({
         "impl": "reference", "metric": "aligned audio-sec/sec (alignment decode path)", "value": round(value, 1),

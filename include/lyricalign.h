@@ -10,10 +10,21 @@
  *   - extern "C", plain pointers and sizes, no C++/torch types. `stream` is a cudaStream_t
  *     passed as void* (NULL = legacy default stream).
  *   - Every function returns 0 on success or a negative la_status; nothing throws.
- *   - The library never allocates device memory behind the caller's back on the data path:
- *     a plan owns a few KB of device metadata created in la_plan_create(); the big buffers
- *     (emission matrix, packed backpointers) live in a caller-provided workspace whose size
- *     la_plan_workspace_bytes() reports.
+ *   - The big buffers (emission matrix, packed backpointers, K1 scratch) live in caller-provided
+ *     workspaces whose sizes la_plan_workspace_bytes() / la_logmel_workspace_bytes() report; the
+ *     device-pointer entry points (la_emit, la_viterbi, la_align, la_logmel*) enqueue on the caller's
+ *     stream and allocate nothing.
+ *   - Cached state (everything the library keeps between calls; la_shutdown() releases it all):
+ *       * plan metadata: a few KB of device memory per plan, taken from a per-device pool of 64 KiB
+ *         blocks by la_plan_create() and returned by la_plan_destroy();
+ *       * K1's constant DFT basis table (520 KB per device, built on the first la_logmel* call);
+ *       * the host-path context of la_align_host() (two staging buffers, a workspace, a pinned result
+ *         buffer and two streams per device; grown on demand, calls on one device are serialised).
+ *     There is no other process-wide mutable state; entry points are re-entrant across threads/streams.
+ *   - Lifetime: la_plan_destroy() may be called while work enqueued with the plan is still running --
+ *     the plan's metadata block is only recycled after an event recorded on the last stream the plan
+ *     was used on has completed. The WORKSPACE and the in/out buffers are the caller's and must outlive
+ *     the enqueued work as usual.
  *   - There is NO CPU fallback. Without a CUDA device every compute entry returns
  *     LA_ERR_CUDA.
  *
@@ -63,13 +74,10 @@ typedef enum la_utt_status {
 typedef struct la_plan la_plan;
 
 const char* la_version(void);
-/* Process-wide SM budgets, for running K1 and K2 CONCURRENTLY on two streams (they are persistent
- * kernels sized to the whole chip by default, so one would otherwise queue behind the other):
- * K1 launches at most `logmel_ctas` CTAs (one per SM, 0 = all SMs), K2 sizes its grid for
- * `emit_sms` SMs (0 = all). Launch K1 first; its CTAs occupy whole SMs (220 KB of shared memory), K2's
- * then fill the rest. */
-void la_set_sm_budget(int logmel_ctas, int emit_sms);
 const char* la_last_error(void);            /* thread-local, human readable */
+/* Frees every cache listed under "Cached state" above on all devices (waits for the host-path streams
+ * first). Live plans stay valid. Safe to call more than once; the caches are rebuilt on demand. */
+void la_shutdown(void);
 int la_device_count(void);
 
 /* ---- plan: shapes + labels of one batch ------------------------------------------------

@@ -18,7 +18,7 @@ _c_int, _i32p, _i64, _vp, _sz = ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, c
 SIGNATURES = {
     "la_version": (ctypes.c_char_p, []),
     "la_last_error": (ctypes.c_char_p, []),
-    "la_set_sm_budget": (None, [_c_int, _c_int]),
+    "la_shutdown": (None, []),
     "la_device_count": (_c_int, []),
     "la_plan_create": (_c_int, [ctypes.POINTER(_vp), _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int]),
     "la_plan_destroy": (None, [_vp]),

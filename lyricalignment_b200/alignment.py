@@ -25,7 +25,7 @@ from . import _lib
 from ._lib import MODE_CE, MODE_CTC, MODE_LOGP
 
 __all__ = ["perform_viterbi_ctc", "perform_viterbi", "run_viterbi_core", "get_mae", "align",
-           "align_clips", "AlignResult", "AlignPlan"]
+           "align_clips", "align_clips_async", "AlignJob", "AlignResult", "AlignPlan"]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -33,24 +33,48 @@ __all__ = ["perform_viterbi_ctc", "perform_viterbi", "run_viterbi_core", "get_ma
 # ----------------------------------------------------------------------------------------------
 def _label_rows(labels) -> List[np.ndarray]:
     """utils/alignment.py:141: keep everything that is not the -100 padding."""
+    lens, flat = _flatten_labels(labels)
+    out, p = [], 0
+    for n in lens.tolist():
+        out.append(flat[p:p + n])
+        p += n
+    return out
+
+
+def _flatten_labels(labels):
+    """-> (lens int32 [B], flat int64 [sum lens]) with the -100 padding stripped (utils/alignment.py:141),
+    in one vectorised pass: the reference's per-element tensor loop costs ~1 ms per clip; a per-row numpy
+    loop would still cost milliseconds per 2 000-clip batch once the kernels take 16 ms."""
     if torch.is_tensor(labels):
         labels = labels.detach().cpu().numpy()
     if isinstance(labels, np.ndarray) and labels.ndim == 2:
         lab = labels.astype(np.int64, copy=False)
-        return [r[r != -100] for r in lab]
-    rows = []
-    for row in labels:
-        r = np.asarray(row, dtype=np.int64).reshape(-1)
-        rows.append(r[r != -100])
-    return rows
+        keep = lab != -100
+        return keep.sum(axis=1).astype(np.int32), lab[keep]
+    rows = [r if (isinstance(r, np.ndarray) and r.dtype == np.int64 and r.ndim == 1)
+            else np.asarray(r, dtype=np.int64).reshape(-1) for r in labels]
+    if not rows:
+        return np.zeros(0, np.int32), np.zeros(0, np.int64)
+    lens = np.fromiter((r.size for r in rows), dtype=np.int64, count=len(rows))
+    flat = np.concatenate(rows) if int(lens.sum()) else np.zeros(0, np.int64)
+    keep = flat != -100
+    if not keep.all():
+        row_of = np.repeat(np.arange(len(rows)), lens)
+        lens = np.bincount(row_of[keep], minlength=len(rows))
+        flat = flat[keep]
+    return lens.astype(np.int32), flat
 
 
-def _resolve_columns(rows: Sequence[np.ndarray], ncols: int):
+def _resolve_columns(rows, ncols: int):
     """Label c indexes column c-1 of the reference's sliced emission matrix (ncols wide), i.e.
     ORIGINAL logit column (c-1)+1. numpy/numba wrap a negative index once (c <= 0); anything else
-    out of range would be an out-of-bounds read in the reference's nopython kernel -- refused."""
-    lens = np.array([len(r) for r in rows], dtype=np.int32)
-    flat = np.concatenate(rows) if len(rows) and lens.sum() else np.zeros(0, np.int64)
+    out of range would be an out-of-bounds read in the reference's nopython kernel -- refused.
+    `rows`: a list of label rows, or the (lens, flat) pair of _flatten_labels."""
+    if isinstance(rows, tuple):
+        lens, flat = rows
+    else:
+        lens = np.array([len(r) for r in rows], dtype=np.int32)
+        flat = np.concatenate(rows) if len(rows) and lens.sum() else np.zeros(0, np.int64)
     col = flat - 1
     col = np.where(col < 0, col + ncols, col)
     if col.size and (col.min() < 0 or col.max() >= ncols):
@@ -128,37 +152,95 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_pinned_pool: dict = {}          # size class -> [pinned uint8 tensors]; cudaHostAlloc costs ~100 us, a 2 000-clip batch 16 ms
+
+
+def _pinned_take(nbytes: int) -> torch.Tensor:
+    cls = 1 << max(12, (nbytes - 1).bit_length())
+    free = _pinned_pool.setdefault(cls, [])
+    return free.pop() if free else torch.empty(cls, dtype=torch.uint8, pin_memory=True)
+
+
+def _pinned_give(buf: torch.Tensor) -> None:
+    free = _pinned_pool.setdefault(buf.numel(), [])
+    if len(free) < 8:
+        free.append(buf)
+
+
+class AlignJob:
+    """K2 + K3 enqueued on the current stream, results on their way to a pinned host buffer.
+    ``result()`` waits for THIS job only (an event), so the host can prepare the next batch -- label
+    flattening, plan creation -- while the kernels of this one run. Owns the plan until then."""
+
+    def __init__(self, plan: AlignPlan, logits2d: torch.Tensor, sil: torch.Tensor | None = None,
+                 keep_workspace: bool = False, timing=None):
+        """timing: optional (start, end) torch.cuda.Event pair recorded around K2 (the benchmark's roofline leg);
+        K2 and K3 are then enqueued as la_emit + la_viterbi instead of la_align -- the same two kernels."""
+        lib = _lib.load()
+        dev = logits2d.device
+        assert logits2d.dtype == torch.float32 and logits2d.stride(1) == 1
+        if logits2d.data_ptr() % 16:
+            logits2d = logits2d.clone()
+        ld = logits2d.stride(0) if logits2d.shape[0] > 1 else max(logits2d.stride(0), plan.V)
+        self.plan = plan
+        self._logits = logits2d                       # keep the inputs alive while the kernels run
+        self.ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
+        # one packed result buffer -> one D2H: [score f64 x B | first i32 x L | last i32 x L | status i32 x B]
+        B, Ltot = max(plan.n_utt, 1), max(plan.total_labels, 1)
+        self._B, self._Ltot = B, Ltot
+        nbytes = 8 * B + 4 * (2 * Ltot + B)
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        score = packed[:8 * B].view(torch.float64)
+        ints = packed[8 * B:].view(torch.int32)
+        first, last, status = ints[:Ltot], ints[Ltot:2 * Ltot], ints[2 * Ltot:2 * Ltot + B]
+        stream = _stream_ptr(dev)
+        if plan.mode == MODE_LOGP or timing is not None:
+            if timing is not None:
+                timing[0].record(torch.cuda.current_stream(dev))
+            _lib.check(lib.la_emit(plan.handle, logits2d.data_ptr(), ld, sil.data_ptr() if sil is not None else None,
+                                   sil.stride(0) if sil is not None else 0, self.ws.data_ptr(), stream), "la_emit")
+            if timing is not None:
+                timing[1].record(torch.cuda.current_stream(dev))
+            _lib.check(lib.la_viterbi(plan.handle, self.ws.data_ptr(), first.data_ptr(), last.data_ptr(),
+                                      score.data_ptr(), status.data_ptr(), stream), "la_viterbi")
+        else:
+            _lib.check(lib.la_align(plan.handle, logits2d.data_ptr(), ld, self.ws.data_ptr(), first.data_ptr(),
+                                    last.data_ptr(), score.data_ptr(), status.data_ptr(), stream), "la_align")
+        self._pinned = _pinned_take(nbytes)
+        self._pinned[:nbytes].copy_(packed, non_blocking=True)
+        self._packed = packed
+        self._nbytes = nbytes
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(dev))
+        self._keep_ws = keep_workspace
+        self._res = None
+
+    def done(self) -> bool:
+        return self._res is not None or self._event.query()
+
+    def result(self) -> AlignResult:
+        if self._res is None:
+            self._event.synchronize()
+            plan, B, Ltot = self.plan, self._B, self._Ltot
+            host = self._pinned[:self._nbytes].numpy().copy()      # the pinned buffer goes back to the pool
+            _pinned_give(self._pinned)
+            h_score = host[:8 * B].view(np.float64)
+            h_int = host[8 * B:].view(np.int32)
+            self._res = AlignResult(h_int[:plan.total_labels], h_int[Ltot:Ltot + plan.total_labels],
+                                    h_score[:plan.n_utt], h_int[2 * Ltot:2 * Ltot + plan.n_utt], plan.l_len)
+            self._pinned = self._packed = self._logits = None
+            if not self._keep_ws:
+                self.ws = None
+                plan.close()
+        return self._res
+
+
 def _run_device(plan: AlignPlan, logits2d: torch.Tensor, sil: torch.Tensor | None = None,
                 keep_workspace: bool = False):
     """logits2d: CUDA float32 [sum T, V] with unit column stride."""
-    lib = _lib.load()
-    dev = logits2d.device
-    assert logits2d.dtype == torch.float32 and logits2d.stride(1) == 1
-    if logits2d.data_ptr() % 16:
-        logits2d = logits2d.clone()
-    ld = logits2d.stride(0) if logits2d.shape[0] > 1 else max(logits2d.stride(0), plan.V)
-    ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
-    # one packed result buffer -> one D2H: [score f64 x B | first i32 x L | last i32 x L | status i32 x B]
-    B, Ltot = max(plan.n_utt, 1), max(plan.total_labels, 1)
-    packed = torch.empty(8 * B + 4 * (2 * Ltot + B), dtype=torch.uint8, device=dev)
-    score = packed[:8 * B].view(torch.float64)
-    ints = packed[8 * B:].view(torch.int32)
-    first, last, status = ints[:Ltot], ints[Ltot:2 * Ltot], ints[2 * Ltot:2 * Ltot + B]
-    stream = _stream_ptr(dev)
-    if plan.mode == MODE_LOGP:
-        _lib.check(lib.la_emit(plan.handle, logits2d.data_ptr(), ld, sil.data_ptr(), sil.stride(0),
-                               ws.data_ptr(), stream), "la_emit")
-        _lib.check(lib.la_viterbi(plan.handle, ws.data_ptr(), first.data_ptr(), last.data_ptr(),
-                                  score.data_ptr(), status.data_ptr(), stream), "la_viterbi")
-    else:
-        _lib.check(lib.la_align(plan.handle, logits2d.data_ptr(), ld, ws.data_ptr(), first.data_ptr(),
-                                last.data_ptr(), score.data_ptr(), status.data_ptr(), stream), "la_align")
-    host = packed.cpu().numpy()
-    h_score = host[:8 * B].view(np.float64)
-    h_int = host[8 * B:].view(np.int32)
-    res = AlignResult(h_int[:plan.total_labels], h_int[Ltot:Ltot + plan.total_labels],
-                      h_score[:plan.n_utt], h_int[2 * Ltot:2 * Ltot + plan.n_utt], plan.l_len)
-    return (res, ws) if keep_workspace else res
+    job = AlignJob(plan, logits2d, sil, keep_workspace=True)
+    res = job.result()
+    return (res, job.ws) if keep_workspace else res
 
 
 def _run_host(plan: AlignPlan, logits2d: torch.Tensor, staging_bytes: int = 0) -> AlignResult:
@@ -187,11 +269,13 @@ def align(prediction, labels, mode: int = MODE_CTC, device: int | None = None) -
     if prediction.dtype != torch.float32:
         prediction = prediction.float()
     B, T, V = prediction.shape
-    rows = _label_rows(labels)
-    if len(rows) < B:
+    lens, flat = _flatten_labels(labels)
+    if len(lens) < B:
         raise IndexError("fewer label rows than batch items")
-    rows = rows[:B]
-    l_len, cols = _resolve_columns(rows, V - 2 if mode == MODE_CTC else V - 1)
+    if len(lens) > B:
+        flat = flat[:int(lens[:B].sum())]
+        lens = lens[:B]
+    l_len, cols = _resolve_columns((lens, flat), V - 2 if mode == MODE_CTC else V - 1)
     if prediction.is_cuda:
         dev = prediction.device.index
         with torch.cuda.device(dev):
@@ -219,11 +303,11 @@ def align_clips(logits2d: torch.Tensor, t_len, labels, mode: int = MODE_CTC, dev
     if logits2d.dim() != 2 or logits2d.dtype != torch.float32:
         raise ValueError("logits2d must be float32 [frames, vocab]")
     V = logits2d.shape[1]
-    rows = _label_rows(labels)
+    lens, flat = _flatten_labels(labels)
     t_len = np.ascontiguousarray(t_len, dtype=np.int32)
-    if len(rows) != len(t_len) or int(t_len.sum()) != logits2d.shape[0]:
+    if len(lens) != len(t_len) or int(t_len.sum()) != logits2d.shape[0]:
         raise ValueError("t_len / labels do not match the logits")
-    l_len, cols = _resolve_columns(rows, V - 2 if mode == MODE_CTC else V - 1)
+    l_len, cols = _resolve_columns((lens, flat), V - 2 if mode == MODE_CTC else V - 1)
     if logits2d.is_cuda:
         dev = logits2d.device.index
         with torch.cuda.device(dev):
@@ -238,6 +322,29 @@ def align_clips(logits2d: torch.Tensor, t_len, labels, mode: int = MODE_CTC, dev
         return _run_host(plan, logits2d.contiguous(), staging_bytes)
     finally:
         plan.close()
+
+
+def align_clips_async(logits2d: torch.Tensor, t_len, labels, mode: int = MODE_CTC, timing=None) -> AlignJob:
+    """``align_clips`` for CUDA logits without the wait: enqueues K2 + K3 + the result copy on the current
+    stream and returns at once. Call ``.result()`` when the alignment is needed; keep one or two jobs in
+    flight and the host-side work of the next batch (labels, plan) hides behind the kernels of this one."""
+    _require_cuda()
+    if logits2d.dim() != 2 or logits2d.dtype != torch.float32 or not logits2d.is_cuda:
+        raise ValueError("logits2d must be CUDA float32 [frames, vocab]")
+    V = logits2d.shape[1]
+    lens, flat = _flatten_labels(labels)
+    t_len = np.ascontiguousarray(t_len, dtype=np.int32)
+    if len(lens) != len(t_len) or int(t_len.sum()) != logits2d.shape[0]:
+        raise ValueError("t_len / labels do not match the logits")
+    l_len, cols = _resolve_columns((lens, flat), V - 2 if mode == MODE_CTC else V - 1)
+    dev = logits2d.device.index
+    with torch.cuda.device(dev):
+        plan = AlignPlan(mode, V, t_len, l_len, cols, dev)
+        try:
+            return AlignJob(plan, logits2d if logits2d.stride(1) == 1 else logits2d.contiguous(), timing=timing)
+        except Exception:
+            plan.close()
+            raise
 
 
 def onoff_seconds(res: AlignResult, hop_size_second: float = 0.02):

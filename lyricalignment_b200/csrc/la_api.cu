@@ -28,8 +28,7 @@ static int cuda_fail(cudaError_t e, const char* where) {
 
 namespace la {
 int set_error(int code, const char* msg) { return fail(code, msg); }
-int g_logmel_ctas = 0;
-int g_emit_sms = 0;
+void logmel_release_tables();
 }
 
 // K3 launch shapes: one pair (blank + label state) per lane wherever possible -- the frame step is a
@@ -60,6 +59,10 @@ struct la_plan {
     bool meta_pooled = false;
     la::BatchMeta meta{};
     const int32_t* d_order[kBuckets] = {nullptr};
+    // the last stream work of this plan was enqueued on: la_plan_destroy() records an event there so the
+    // pooled metadata block is not handed to another plan while K2/K3 may still be reading it
+    mutable cudaStream_t last_stream = nullptr;
+    mutable bool used = false;
 };
 
 // Host-path context (la_align_host): one per device, grown on demand, reused across plans so a
@@ -83,10 +86,11 @@ static HostCtx g_host[64];
 // sync) cost milliseconds next to a 40 MB clip, and the reference's entry points decode one clip
 // per call.
 constexpr size_t kMetaBlock = 64 << 10;
+struct PoolBlock { void* p; cudaEvent_t busy; };   // busy == nullptr: free right away
 struct DevInfo {
     std::mutex mu;
     int sm_count = 0;
-    std::vector<void*> free_blocks;
+    std::vector<PoolBlock> free_blocks;
 };
 static DevInfo g_dev[64];
 
@@ -95,7 +99,16 @@ static int meta_alloc(int device, size_t bytes, void** out, bool* pooled) {
     if (bytes <= kMetaBlock) {
         std::lock_guard<std::mutex> lock(D.mu);
         *pooled = true;
-        if (!D.free_blocks.empty()) { *out = D.free_blocks.back(); D.free_blocks.pop_back(); return LA_OK; }
+        for (size_t i = D.free_blocks.size(); i-- > 0;) {
+            PoolBlock& b = D.free_blocks[i];
+            if (b.busy) {
+                if (cudaEventQuery(b.busy) != cudaSuccess) { cudaGetLastError(); continue; }   // its last user is still running
+                cudaEventDestroy(b.busy);
+            }
+            *out = b.p;
+            D.free_blocks.erase(D.free_blocks.begin() + (long)i);
+            return LA_OK;
+        }
         LA_CUDA(cudaMalloc(out, kMetaBlock));
         return LA_OK;
     }
@@ -103,11 +116,23 @@ static int meta_alloc(int device, size_t bytes, void** out, bool* pooled) {
     LA_CUDA(cudaMalloc(out, bytes));
     return LA_OK;
 }
-static void meta_free(int device, void* p, bool pooled) {
+// `stream`/`used`: where the plan's kernels were last enqueued. A pooled block goes back with an event
+// recorded there and is only reused once that event has completed; cudaFree synchronises by itself.
+static void meta_free(int device, void* p, bool pooled, cudaStream_t stream = nullptr, bool used = false) {
     if (!p) return;
     if (pooled) {
+        cudaEvent_t ev = nullptr;
+        if (used) {
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventRecord(ev, stream) != cudaSuccess) {
+                cudaGetLastError();
+                if (ev) cudaEventDestroy(ev);
+                ev = nullptr;
+                cudaDeviceSynchronize();          // could not fence the block: wait for everything instead
+            }
+        }
         std::lock_guard<std::mutex> lock(g_dev[device].mu);
-        g_dev[device].free_blocks.push_back(p);
+        g_dev[device].free_blocks.push_back(PoolBlock{p, ev});
     } else {
         cudaFree(p);
     }
@@ -129,11 +154,53 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 extern "C" {
 
 const char* la_version(void) { return "lyricalign-b200 0.1 (sm_100a)"; }
-void la_set_sm_budget(int logmel_ctas, int emit_sms) {
-    la::g_logmel_ctas = logmel_ctas > 0 ? logmel_ctas : 0;
-    la::g_emit_sms = emit_sms > 0 ? emit_sms : 0;
-}
 const char* la_last_error(void) { return g_err.c_str(); }
+
+// Releases everything the library caches between calls (see lyricalign.h "Cached state"): the host-path
+// staging context of every device, the pooled plan-metadata blocks, K1's basis tables. Plans that are
+// still alive stay valid (their metadata blocks are theirs until la_plan_destroy).
+void la_shutdown(void) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return; }
+    for (int d = 0; d < 64; ++d) {
+        HostCtx& C = g_host[d];
+        {
+            std::lock_guard<std::mutex> lock(C.mu);
+            if (C.s_copy || C.d_ws || C.d_out || C.h_out || C.d_stage[0]) {
+                cudaSetDevice(d);
+                if (C.s_copy) cudaStreamSynchronize(C.s_copy);
+                if (C.s_comp) cudaStreamSynchronize(C.s_comp);
+                for (int i = 0; i < 2; ++i) {
+                    if (C.d_stage[i]) cudaFree(C.d_stage[i]);
+                    if (C.ev_copied[i]) cudaEventDestroy(C.ev_copied[i]);
+                    if (C.ev_done[i]) cudaEventDestroy(C.ev_done[i]);
+                    C.d_stage[i] = nullptr; C.ev_copied[i] = nullptr; C.ev_done[i] = nullptr;
+                }
+                if (C.d_ws) cudaFree(C.d_ws);
+                if (C.d_out) cudaFree(C.d_out);
+                if (C.h_out) cudaFreeHost(C.h_out);
+                if (C.s_copy) cudaStreamDestroy(C.s_copy);
+                if (C.s_comp) cudaStreamDestroy(C.s_comp);
+                C.d_ws = C.d_out = C.h_out = nullptr;
+                C.s_copy = C.s_comp = nullptr;
+                C.stage_bytes = C.ws_bytes = C.out_bytes = C.h_out_bytes = 0;
+            }
+        }
+        DevInfo& D = g_dev[d];
+        std::lock_guard<std::mutex> lock(D.mu);
+        if (!D.free_blocks.empty()) {
+            cudaSetDevice(d);
+            for (PoolBlock& b : D.free_blocks) {
+                if (b.busy) { cudaEventSynchronize(b.busy); cudaEventDestroy(b.busy); }
+                cudaFree(b.p);
+            }
+            D.free_blocks.clear();
+        }
+    }
+    la::logmel_release_tables();
+    cudaSetDevice(cur);
+    cudaGetLastError();
+}
 int la_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -250,7 +317,10 @@ extern "C" {
 
 void la_plan_destroy(la_plan* P) {
     if (!P) return;
-    meta_free(P->device, P->d_meta, P->meta_pooled);
+    int cur = -1;
+    if (P->used && cudaGetDevice(&cur) == cudaSuccess && cur != P->device) cudaSetDevice(P->device); else cur = -1;
+    meta_free(P->device, P->d_meta, P->meta_pooled, P->last_stream, P->used);
+    if (cur >= 0) cudaSetDevice(cur);
     delete P;
 }
 
@@ -307,8 +377,10 @@ static int viterbi_impl(const la_plan* P, void* d_ws, int32_t* d_first, int32_t*
         vp.chunk = la::viterbi_chunk_frames(P->row_max[b]);
         vp.first = d_first; vp.last_plus1 = d_last; vp.score = d_score; vp.status = d_status;
         vp.dp_dump = d_dp;
-        LA_CUDA(la::launch_viterbi(vp, kShape[b].K, P->warps_max[b], true, static_cast<cudaStream_t>(stream)));
+        LA_CUDA(la::launch_viterbi(vp, kShape[b].K, P->warps_max[b], static_cast<cudaStream_t>(stream)));
     }
+    P->last_stream = static_cast<cudaStream_t>(stream);
+    P->used = true;
     return LA_OK;
 }
 
@@ -403,23 +475,30 @@ int la_align_host(la_plan* P, const float* h_logits, int64_t ld, int32_t* h_firs
     while (row < P->total_T) {
         const int64_t n = std::min<int64_t>((int64_t)rows_per_stage, P->total_T - row);
         const int sbuf = i & 1;
-        if (used[sbuf]) LA_CUDA(cudaStreamWaitEvent(C.s_copy, C.ev_done[sbuf], 0));
-        LA_CUDA(cudaMemcpyAsync(C.d_stage[sbuf], h_logits + row * ld, (size_t)n * row_bytes,
-                                cudaMemcpyHostToDevice, C.s_copy));
-        LA_CUDA(cudaEventRecord(C.ev_copied[sbuf], C.s_copy));
-        LA_CUDA(cudaStreamWaitEvent(C.s_comp, C.ev_copied[sbuf], 0));
+        // a failure must not leave queued work reading the staging buffers the next call will overwrite
+#define LA_CUDA_DRAIN(x)                                                                            \
+        do {                                                                                        \
+            cudaError_t e__ = (x);                                                                  \
+            if (e__ != cudaSuccess) { cudaStreamSynchronize(C.s_copy); cudaStreamSynchronize(C.s_comp); return cuda_fail(e__, #x); } \
+        } while (0)
+        if (used[sbuf]) LA_CUDA_DRAIN(cudaStreamWaitEvent(C.s_copy, C.ev_done[sbuf], 0));
+        LA_CUDA_DRAIN(cudaMemcpyAsync(C.d_stage[sbuf], h_logits + row * ld, (size_t)n * row_bytes,
+                                      cudaMemcpyHostToDevice, C.s_copy));
+        LA_CUDA_DRAIN(cudaEventRecord(C.ev_copied[sbuf], C.s_copy));
+        LA_CUDA_DRAIN(cudaStreamWaitEvent(C.s_comp, C.ev_copied[sbuf], 0));
         rc = emit_rows(P, static_cast<const float*>(C.d_stage[sbuf]), ld, nullptr, 0, C.d_ws, row, n, C.s_comp);
-        if (rc) return rc;
-        LA_CUDA(cudaEventRecord(C.ev_done[sbuf], C.s_comp));
+        if (rc) { cudaStreamSynchronize(C.s_copy); cudaStreamSynchronize(C.s_comp); return rc; }
+        LA_CUDA_DRAIN(cudaEventRecord(C.ev_done[sbuf], C.s_comp));
         used[sbuf] = true;
         row += n;
         ++i;
     }
     rc = la_viterbi(P, C.d_ws, d_first, d_last, d_score, d_status, C.s_comp);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(C.s_copy); cudaStreamSynchronize(C.s_comp); return rc; }
     // one D2H of the packed results into the pinned bounce buffer, then scatter on the host
-    LA_CUDA(cudaMemcpyAsync(C.h_out, C.d_out, out_bytes - 64, cudaMemcpyDeviceToHost, C.s_comp));
-    LA_CUDA(cudaStreamSynchronize(C.s_comp));
+    LA_CUDA_DRAIN(cudaMemcpyAsync(C.h_out, C.d_out, out_bytes - 64, cudaMemcpyDeviceToHost, C.s_comp));
+    LA_CUDA_DRAIN(cudaStreamSynchronize(C.s_comp));
+#undef LA_CUDA_DRAIN
     const unsigned char* h = static_cast<const unsigned char*>(C.h_out);
     if (P->total_L > 0) {
         memcpy(h_first, h, (size_t)P->total_L * 4);
@@ -443,6 +522,8 @@ static int emit_rows(const la_plan* P, const float* d_logits, int64_t ld, const 
     ep.row0 = row0;
     { static const int hint = [] { const char* e = getenv("LA_EMIT_L2_HINT"); return e ? atoi(e) : 0; }(); ep.l2_hint = hint; }
     ep.n_rows = (int)n_rows;
-    LA_CUDA(la::launch_emit(ep, la::g_emit_sms > 0 ? std::min(la::g_emit_sms, P->sm_count) : P->sm_count, stream));
+    LA_CUDA(la::launch_emit(ep, P->sm_count, stream));
+    P->last_stream = stream;
+    P->used = true;
     return LA_OK;
 }

@@ -111,6 +111,9 @@ struct VitParams {
     int n_order;
     int row_floats_max;     // widest emission row in the bucket (smem stage sizing)
     int chunk;              // frames per TMA chunk
+    int stages;             // emission stages in shared memory (set by launch_viterbi)
+    int ring;               // hand-off ring slots per warp boundary (set by launch_viterbi)
+    int trace;              // LA_VIT_TRACE: CTA 0 records its phase clocks (perf triage)
     int32_t* first;
     int32_t* last_plus1;
     double* score;
@@ -119,11 +122,10 @@ struct VitParams {
 };
 
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
-cudaError_t launch_viterbi(const VitParams& p, int K, int warps, bool wide, cudaStream_t stream);
+cudaError_t launch_viterbi(const VitParams& p, int K, int warps, cudaStream_t stream);
 int viterbi_chunk_frames(int row_floats_max);
 int set_error(int code, const char* msg);
-extern int g_logmel_ctas;   // la_set_sm_budget(): 0 = whole chip
-extern int g_emit_sms;   // records la_last_error(), returns code
+// set_error records la_last_error() and returns code
 
 constexpr double kFloor = -10000000.0;   // utils/alignment.py:144
 constexpr float kClip = -1000.0f;        // utils/alignment.py:132,134 / :18,20

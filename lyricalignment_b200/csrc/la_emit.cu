@@ -277,8 +277,14 @@ size_t emit_smem_bytes(int stages) {
 template <int MODE, int STAGES, int CTAS>
 static cudaError_t launch_emit_variant(const EmitParams& p, int sm_count, cudaStream_t stream) {
     const size_t smem = emit_smem_bytes(STAGES);
-    cudaError_t e = cudaFuncSetAttribute(emit_kernel<MODE, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    static bool attr_done[64] = {};               // per-function, per-device opt-in: set once, not per launch
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(emit_kernel<MODE, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done[dev] = true;
+    }
     int grid = CTAS * sm_count;
     if (grid > p.n_rows) grid = p.n_rows;
     emit_kernel<MODE, STAGES, CTAS><<<grid, kEmitThreads, smem, stream>>>(p);
@@ -291,13 +297,9 @@ cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream) 
         gather_logp_kernel<<<p.n_rows, 128, 0, stream>>>(p);
         return cudaGetLastError();
     }
-    // Default: 3 CTAs/SM with 4-stage rings. Measured A/B on one box (profiles/k2_tuning_r1.md): with the
-    // SM clock power-capped to ~1.7 GHz (the tensor-heavy K1 runs right before), 2 CTAs x 6 stages fell to
-    // 0.90 of the HBM peak (consumer latency-bound), 3 CTAs x 4 stages holds 0.98. LA_EMIT_VARIANT=0 selects
-    // the old shape for comparison.
-    static const int variant = [] { const char* e = getenv("LA_EMIT_VARIANT"); return e ? atoi(e) : 1; }();
-    if (variant == 0)
-        return p.m.mode == 0 ? launch_emit_variant<0, 6, 2>(p, sm_count, stream) : launch_emit_variant<1, 6, 2>(p, sm_count, stream);
+    // 3 CTAs/SM with 4-stage rings. Measured A/B on one box (profiles/k2_tuning_r1.md): with the SM clock
+    // power-capped to ~1.7 GHz (the tensor-heavy K1 runs right before), 2 CTAs x 6 stages fell to 0.90 of the
+    // HBM peak (consumer latency-bound), 3 CTAs x 4 stages holds 0.98; the slower shape is no longer built.
     return p.m.mode == 0 ? launch_emit_variant<0, 4, 3>(p, sm_count, stream) : launch_emit_variant<1, 4, 3>(p, sm_count, stream);
 }
 

@@ -121,18 +121,25 @@ struct LogmelParams {
     const __half* basis;          // [pass 2][k-step 13][slice 3] canonical UMMA K-major blocks
     int* group_max;               // running maxima of the mel power (bit pattern of a float >= 0)
     int* tile_min;                // per-tile minima of the mel power (same encoding)
-    int dbg;                      // LA_LOGMEL_DBG: 8 = CTA 0 timestamps its first tiles (perf triage), 16 = swap the fp16 pair order (bring-up)
+    int dbg;                      // LA_LOGMEL_DBG (perf triage only; 32.. break the numerics): 8 = CTA 0 timestamps its first tiles, 16 = swap the fp16 pair
+                                  // order, 32 = alternate accumulators, 64 = no tcgen05.st, 128 = no epilogue math, 256 = no tile-scale scan
 };
 
-// LA_LOGMEL_DBG & 8: CTA 0 timestamps its first 8 tiles (perf triage only)
-__device__ unsigned long long g_trace[4 * 8 * 32];
-__device__ __forceinline__ void trace(int dbg, int role, uint32_t tl, int ev) {
-    if ((dbg & 8) && blockIdx.x == 0 && tl < 8) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_trace[(role * 8 + tl) * 32 + ev] = t;
+// LA_LOGMEL_DBG & 8 launches the TRACE instantiation: CTA 0 timestamps its first 8 tiles (perf triage only;
+// compiled out of the production kernel)
+constexpr int kTraceEvents = 64;
+__device__ unsigned long long g_trace[4 * 8 * kTraceEvents];
+template <bool TRACE>
+__device__ __forceinline__ void trace_ev(int role, uint32_t tl, int ev) {
+    if constexpr (TRACE) {
+        if (blockIdx.x == 0 && tl < 8) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            g_trace[(role * 8 + tl) * kTraceEvents + ev] = t;
+        }
     }
 }
+#define trace(dbg, role, tl, ev) trace_ev<TRACE>(role, tl, ev)
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -155,6 +162,35 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// The issuer warps run warp-uniform code (so ptxas keeps descriptors and addresses in uniform registers: the
+// divergent `if (lane == 0)` form cost six R2UR per MMA, and the issuing thread competes for issue slots with
+// six busy warps on its scheduler); one elected lane issues.
+__device__ __forceinline__ void umma_f16_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
+// Ring indexing restarts with every tile (stage = i % n for the tile's k-step i = 0..25), so a fully unrolled
+// tile has compile-time stage indices. Stage s is used upt(s) = ceil((26 - s) / n) times per tile; the phase
+// parity of its next use is therefore (tl * upt(s) + i / n) & 1.
+__device__ __forceinline__ uint32_t ring_parity(uint32_t tl, int i, int n) {
+    const int s = i % n;
+    const int upt = (kIters - s + n - 1) / n;
+    return (tl * (uint32_t)upt + (uint32_t)(i / n)) & 1u;
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
@@ -219,6 +255,7 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {       // eleme
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+template <bool TRACE>
 __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* bstages = smem;
@@ -251,15 +288,21 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    for (int i = tid; i < kRawBytes / 16; i += kLogmelThreads)        // pads / last group's tail must read as 0.0 in the scale scan
+        reinterpret_cast<float4*>(raw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();                                               // generic-proxy zeroes before the async-proxy (TMA) writes
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // all 512 columns are ours (one CTA per SM), so the allocation can only start at lane 0, column 0; using the
+    // literal lets every TMEM address below be an immediate
+    constexpr uint32_t tmem_base = 0;
+    if (*tmem_slot != 0u) __trap();
 
     if (warp == 0) {
         // =============================== producer ==========================================
         if (lane == 0) {
-            uint32_t it = 0, tl = 0;
+            uint32_t tl = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
                 const ClipDesc c = p.clips[p.tile_clip[tile]];
                 const int f0 = (tile - c.tile0) * kTileM;
@@ -288,9 +331,9 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                                          (uint32_t)(min(rn.hi * kRawGroup, kRawRows) - rn.lo * kRawGroup) * kHop * 4);
                 }
                 trace(p.dbg, 3, tl, 1);
-                for (int i = 0; i < kIters; ++i, ++it) {
-                    const int s = it % kBStages;
-                    mbar_wait(&b_empty[s], ((it / kBStages) & 1) ^ 1);
+                for (int i = 0; i < kIters; ++i) {
+                    const int s = i % kBStages;
+                    mbar_wait(&b_empty[s], ring_parity(tl, i, kBStages) ^ 1);
                     trace(p.dbg, 3, tl, 2 + i);
                     mbar_arrive_expect_tx(&b_full[s], kBStageBytes);
                     bulk_g2s(bstages + s * kBStageBytes,
@@ -301,56 +344,60 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
         }
     } else if (warp == 1 || warp == 2) {
         // =============================== MMA issuers =======================================
-        // warp 1: Acc0 += A1*B1 (the exact chain); warp 2: Acc1 += the five cross terms. tcgen05.mma issue is
-        // back-pressured by the tensor pipe; warp 2 waits for the NEXT k-step's operands between its 4th
-        // and 5th MMA, so its barrier bookkeeping overlaps MMAs that are still queued.
-        if (lane == 0) {
-            const bool cross = warp == 2;
-            const uint32_t d_acc = tmem_base + (cross ? kNpad : 0);
-            const uint32_t ta0 = tmem_base + kACol0;
-            const uint32_t bs0 = smem_u32(bstages);
-            uint32_t it = 0, tl = 0;
-            bool ready = false;                       // operands of iteration `it` already awaited
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
-                for (int pass = 0; pass < 2; ++pass) {
-                    const uint32_t ph = 2 * tl + pass;
-                    mbar_wait(tmem_empty, (ph & 1) ^ 1);   // epilogue of the previous pass drained TMEM
+        // warp 1: Acc0 += A1*B1 (the exact chain); warp 2: Acc1 += the five cross terms. Whole warps, uniform
+        // control flow, one elected lane issues; the tile's 26 k-steps are fully unrolled so every stage
+        // index, TMEM column and descriptor offset is an immediate. warp 2 waits for the NEXT k-step's
+        // operands between its 4th and 5th MMA, so its barrier bookkeeping overlaps MMAs still queued.
+        const bool cross = warp == 2;
+        const uint32_t d_acc = tmem_base + (cross ? kNpad : 0);
+        const uint32_t ta0 = tmem_base + kACol0;
+        const uint64_t bd0 = umma_desc(smem_u32(bstages), kBLbo, 128);
+        uint32_t tl = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+                const int pass = i / kKSteps, ks = i % kKSteps;
+                const int sb = i % kBStages, sa = i % kAStages;
+                if (ks == 0) {
+                    mbar_wait(tmem_empty, ((2 * tl + pass) & 1) ^ 1);   // epilogue of the previous pass drained TMEM
                     tc_fence_after();
-                    if (cross) trace(p.dbg, 0, tl, pass ? 29 : 0);
-                    for (int ks = 0; ks < kKSteps; ++ks, ++it) {
-                        const int sb = it % kBStages, sa = it % kAStages;
-                        if (!ready) {
-                            mbar_wait(&b_full[sb], (it / kBStages) & 1);
-                            mbar_wait(&a_full[sa], (it / kAStages) & 1);
-                            tc_fence_after();
-                        }
-                        ready = false;
-                        if (cross) trace(p.dbg, 0, tl, 1 + pass * kKSteps + ks);
-                        const uint32_t a1 = ta0 + sa * kAStageCols, a2 = a1 + 8, a3 = a1 + 16;
-                        const uint64_t b1 = umma_desc(bs0 + sb * kBStageBytes, kBLbo, 128);
-                        const uint64_t b2 = umma_desc(bs0 + sb * kBStageBytes + kBBytes, kBLbo, 128);
-                        const uint64_t b3 = umma_desc(bs0 + sb * kBStageBytes + 2 * kBBytes, kBLbo, 128);
-                        if (!cross) {
-                            umma_f16_ts(d_acc, a1, b1, kIdesc, ks > 0 ? 1u : 0u);
-                        } else {
-                            umma_f16_ts(d_acc, a3, b1, kIdesc, ks > 0 ? 1u : 0u);   // small terms first
-                            umma_f16_ts(d_acc, a1, b3, kIdesc, 1u);
-                            umma_f16_ts(d_acc, a2, b2, kIdesc, 1u);
-                            umma_f16_ts(d_acc, a2, b1, kIdesc, 1u);
-                            const uint32_t nx = it + 1;
-                            if (nx < (uint32_t)kIters * (tl + 1) || tile + (int)gridDim.x < p.n_tiles) {
-                                mbar_wait(&b_full[nx % kBStages], (nx / kBStages) & 1);
-                                mbar_wait(&a_full[nx % kAStages], (nx / kAStages) & 1);
-                                tc_fence_after();
-                                ready = true;
-                            }
-                            umma_f16_ts(d_acc, a1, b2, kIdesc, 1u);
-                        }
-                        umma_commit(&a_empty[sa]);
-                        umma_commit(&b_empty[sb]);
+                    if (cross && lane == 0) trace(p.dbg, 0, tl, pass ? 29 : 0);
+                }
+                // warp 2 has already awaited these operands (look-ahead below), except for the tile's first k-step.
+                // (No look-ahead across tiles: k-step 25 and the next tile's k-step 0 share basis stage 0, whose
+                // refill waits for THIS k-step's commits -- waiting for it before committing would deadlock.)
+                if (!cross || i == 0) {
+                    mbar_wait(&b_full[sb], ring_parity(tl, i, kBStages));
+                    mbar_wait(&a_full[sa], ring_parity(tl, i, kAStages));
+                    tc_fence_after();
+                }
+                const uint32_t a1 = ta0 + sa * kAStageCols, a2 = a1 + 8, a3 = a1 + 16;
+                const uint64_t b1 = bd0 + (uint64_t)((sb * kBStageBytes) >> 4);          // start-address field += stage
+                const uint64_t b2 = b1 + (uint64_t)(kBBytes >> 4), b3 = b1 + (uint64_t)((2 * kBBytes) >> 4);
+                if (!cross) {
+                    umma_f16_ts_elect(d_acc, a1, b1, kIdesc, ks > 0 ? 1u : 0u);
+                } else {
+                    if (TRACE && i >= 4 && i < 8 && lane == 0) trace(p.dbg, 0, tl, 32 + (i - 4) * 5);
+                    umma_f16_ts_elect(d_acc, a3, b1, kIdesc, ks > 0 ? 1u : 0u);   // small terms first
+                    umma_f16_ts_elect(d_acc, a1, b3, kIdesc, 1u);
+                    umma_f16_ts_elect(d_acc, a2, b2, kIdesc, 1u);
+                    umma_f16_ts_elect(d_acc, a2, b1, kIdesc, 1u);
+                    if (TRACE && i >= 4 && i < 8 && lane == 0) trace(p.dbg, 0, tl, 33 + (i - 4) * 5);
+                    if (i + 1 < kIters) {
+                        mbar_wait(&b_full[(i + 1) % kBStages], ring_parity(tl, i + 1, kBStages));
+                        mbar_wait(&a_full[(i + 1) % kAStages], ring_parity(tl, i + 1, kAStages));
+                        tc_fence_after();
                     }
-                    umma_commit(tmem_full);
-                    if (cross) trace(p.dbg, 0, tl, 27 + pass);
+                    if (TRACE && i >= 4 && i < 8 && lane == 0) trace(p.dbg, 0, tl, 34 + (i - 4) * 5);
+                    umma_f16_ts_elect(d_acc, a1, b2, kIdesc, 1u);
+                    if (TRACE && i >= 4 && i < 8 && lane == 0) trace(p.dbg, 0, tl, 35 + (i - 4) * 5);
+                }
+                umma_commit_elect(&a_empty[sa]);
+                umma_commit_elect(&b_empty[sb]);
+                if (TRACE && cross && i >= 4 && i < 8 && lane == 0) trace(p.dbg, 0, tl, 36 + (i - 4) * 5);
+                if (ks == kKSteps - 1) {
+                    umma_commit_elect(tmem_full);
+                    if (cross && lane == 0) trace(p.dbg, 0, tl, 27 + pass);
                 }
             }
         }
@@ -401,27 +448,31 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                     }
                 }
             }
-            for (int g = rp.lo; g < rp.hi; ++g) {
-                const int cnt = min(kRawGroup, kRawRows - g * kRawGroup) * kHop;
-                const float4* src = reinterpret_cast<const float4*>(raw + g * kRawGroupPitch);
-                for (int i = xt; i < cnt / 4; i += 512) m = max4abs(src[i], m);
+            {
+                // the TMA-staged groups [lo, hi) are one contiguous range of the staging buffer (the 8-float pads
+                // between groups and the unused tail of the last group were zeroed once at kernel start and are
+                // never written), so the scan is a flat float4 loop: ~11 loads per thread
+                const float4* src = reinterpret_cast<const float4*>(raw);
+                const int i1 = ((p.dbg & 256) ? rp.lo : rp.hi) * (kRawGroupPitch / 4);
+                for (int i = rp.lo * (kRawGroupPitch / 4) + xt; i < i1; i += 512) m = max4abs(src[i], m);
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (lane == 0) wmax[(tl & 1) * 16 + (warp - 12)] = m;
-            named_bar_sync(2, 512);                                 // staging complete, per-warp maxima visible
+            if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 31);
+            named_bar_sync(2, 512);
+            if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 29);                                 // staging complete, per-warp maxima visible
             m = wmax[(tl & 1) * 16 + (lane & 15)];
 #pragma unroll
             for (int o = 8; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             // S = 2^(ex - 125) > 2 max|x| >= |fold|; T = fold * 2^14 / S; X = acc * S * 2^-28
             int ex = (int)(__float_as_uint(m) >> 23);
+            if (p.dbg & 256) ex = 129;
             ex = min(max(ex, 27), 250);
             const float scale_t = __uint_as_float((uint32_t)(266 - ex) << 23);
             if (xt == 0) tile_e[tl & 1] = ex;
             if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 1);
-            const uint32_t it0 = tl * kIters;
-            for (uint32_t it = it0 + ((set - it0) & 3u); it < it0 + kIters; it += 4) {
-                const int local = (int)(it - it0);
+            for (int local = set; local < kIters; local += kAStages) {
                 const int pass = local >= kKSteps ? 1 : 0;
                 const int ks = local - pass * kKSteps;
                 uint32_t pk[24];                                     // [plane 3][column 8], two fp16 per column
@@ -468,10 +519,11 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                     }
                 }
                 // only the stores need the TMEM stage: everything above overlaps the MMAs in flight
-                mbar_wait(&a_empty[set], ((it >> 2) & 1) ^ 1);
+                if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 16 + (local >> 2));
+                mbar_wait(&a_empty[set], ring_parity(tl, local, kAStages) ^ 1);
                 tc_fence_after();
                 if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 2 + (local >> 2));
-                {
+                if (!(p.dbg & 64)) {
                     uint32_t pl[8];
 #pragma unroll
                     for (int pln = 0; pln < 3; ++pln) {
@@ -507,48 +559,29 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
             const int f0 = (tile - c.tile0) * kTileM;
             const int f = f0 + row;
             const bool valid = f < c.n_frames;
-            const int64_t ostride = c.out_stride;
-            float* outp = p.out + c.out_off + f;
-            float mx = 0.f, mn = INFINITY;
             float* sh2 = shared2 + (tl & 1) * 2 * kTileM + row;
             for (int pass = 0; pass < 2; ++pass) {
                 const uint32_t ph = 2 * tl + pass;
                 mbar_wait(tmem_full, ph & 1);
                 tc_fence_after();
                 if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 2 * pass);
-                const float sc = __uint_as_float((uint32_t)(tile_e[tl & 1] - 26) << 23);    // S * 2^-28
-                const float sc2 = sc * sc;
-                int64_t os = ostride;
-                asm volatile("" : "+l"(os));                      // opaque per pass: keeps ptxas from hoisting 60 output pointers out of the pass loop (onto the stack)
+                // The drain is on the tensor pipe's critical path (the next pass cannot start before TMEM is
+                // read out), so it only accumulates: pass 0 parks the Re part of every mel sum in `part`,
+                // pass 1 adds the Im part. log10 and the stores happen after TMEM is released.
                 float* sp = part + (half ? ms : 0) * kTileM + row;
-                float* optr = outp + (half ? ms : 0) * os;        // where the filter held in a0 will be stored
                 float a0 = 0.f, a1 = 0.f;
-                auto emit = [&](float v) {              // v = complete mel power of the filter at optr
-                    if (valid) {
-                        *optr = (log10f(fmaxf(v, 1e-10f)) + 4.0f) / 4.0f;
-                        mx = fmaxf(mx, v);
-                        mn = fminf(mn, v);
-                    }
-                };
                 auto flush = [&]() {                    // the filter held in a0 is complete for this pass
-                    if (pass == 0) *sp = a0;
-                    else emit((*sp + a0) * sc2);
+                    *sp = pass == 0 ? a0 : *sp + a0;
                     sp += kTileM;
-                    optr += os;
                     a0 = a1; a1 = 0.f;
                 };
                 int nshared = 0;
                 auto flush_hi = [&]() {                 // high half: its first two filters are the shared ones
-                    if (nshared < 2) {
-                        float* s2 = sh2 + nshared * kTileM;
-                        *s2 = pass == 0 ? a0 : *s2 + a0;
-                        ++nshared;
-                        sp += kTileM;
-                        optr += os;
-                        a0 = a1; a1 = 0.f;
-                    } else {
-                        flush();
-                    }
+                    float* dst = nshared < 2 ? sh2 + nshared * kTileM : sp;
+                    *dst = pass == 0 ? a0 : *dst + a0;
+                    ++nshared;
+                    sp += kTileM;
+                    a0 = a1; a1 = 0.f;
                 };
                 const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
                 uint32_t c0[16], c1[16];
@@ -577,7 +610,9 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                     if (LAST) release_tmem();                                                         \
                     LA_MEL_CHUNK_##C(LA_BIN)                                                          \
                 }
-                if (!half) {
+                if (p.dbg & 128) {
+                    release_tmem();
+                } else if (!half) {
 #define LA_FLUSH flush
                     LA_CHUNK(0, false) LA_CHUNK(1, false) LA_CHUNK(2, false)
                     LA_CHUNK(3, false) LA_CHUNK(4, false) LA_CHUNK(5, true)
@@ -594,27 +629,43 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 }
 #undef LA_CHUNK
 #undef LA_BIN
+                if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 2 * pass + 1);
                 if (pass == 0) {
                     if (!half) { r_ms0 = a0; r_ms1 = a1; }      // the low half's Re share of filters ms, ms + 1
-                } else {
-                    named_bar_sync(3, 256);                     // both halves: the high half's shares are in shared2
-                    if (!half) {
-                        optr = outp + ms * os;
-                        emit((sh2[0] + r_ms0 + a0) * sc2);
-                        optr += os;
-                        emit((sh2[kTileM] + r_ms1 + a1) * sc2);
+                    continue;
+                }
+                // ---- finish (off the critical path: the next tile's MMAs are already running) ----
+                named_bar_sync(3, 256);                         // the high half's shares of filters ms, ms+1 are in sh2
+                if (!half) {
+                    part[ms * kTileM + row] = sh2[0] + r_ms0 + a0;
+                    part[(ms + 1) * kTileM + row] = sh2[kTileM] + r_ms1 + a1;
+                }
+                named_bar_sync(3, 256);                         // `part` holds the unscaled mel power of the whole tile
+                const float sc = __uint_as_float((uint32_t)(tile_e[tl & 1] - 26) << 23);    // S * 2^-28
+                const float sc2 = sc * sc;
+                float mx = 0.f, mn = INFINITY;
+                if (valid) {
+                    const float* src = part + half * (kMels / 2) * kTileM + row;
+                    float* dst = p.out + c.out_off + f + (int64_t)half * (kMels / 2) * c.out_stride;
+#pragma unroll 8
+                    for (int m = 0; m < kMels / 2; ++m, src += kTileM, dst += c.out_stride) {
+                        const float v = *src * sc2;
+                        *dst = (log10f(fmaxf(v, 1e-10f)) + 4.0f) / 4.0f;
+                        mx = fmaxf(mx, v);
+                        mn = fminf(mn, v);
                     }
                 }
-                if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 2 * pass + 1);
-            }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            }
-            if (lane == 0) {                            // powers are >= 0: int order == float order
-                atomicMax(p.group_max + c.group, __float_as_int(mx));
-                atomicMin(p.tile_min + tile, __float_as_int(mn));
+                for (int o = 16; o; o >>= 1) {
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                }
+                if (lane == 0) {                                // powers are >= 0: int order == float order
+                    atomicMax(p.group_max + c.group, __float_as_int(mx));
+                    atomicMin(p.tile_min + tile, __float_as_int(mn));
+                }
+                named_bar_sync(3, 256);                         // `part` is free for the next tile's pass 0
+                if (warp == 4 && lane == 0) trace(p.dbg, 2, tl, 4);
             }
         }
     }
@@ -820,10 +871,15 @@ static int logmel_run_impl(const float* d_wave, float* d_out, const std::vector<
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const size_t smem = logmel_smem_bytes();
-    e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "smem attr: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
-    const int ctas = la::g_logmel_ctas > 0 ? std::min(la::g_logmel_ctas, sms) : sms;
-    logmel_kernel<<<std::min(n_tiles, ctas), kLogmelThreads, smem, stream>>>(p);
+    static bool attr_done[64] = {};               // per-function, per-device opt-in: set once, not per launch
+    if (device >= 0 && device < 64 && !attr_done[device]) {
+        e = cudaFuncSetAttribute(logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "smem attr: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
+        attr_done[device] = true;
+    }
+    if (p.dbg & 8) logmel_kernel<true><<<std::min(n_tiles, sms), kLogmelThreads, smem, stream>>>(p);
+    else logmel_kernel<false><<<std::min(n_tiles, sms), kLogmelThreads, smem, stream>>>(p);
     logmel_floor_kernel<<<n_tiles, kTileM, 0, stream>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_lm_err, sizeof g_lm_err, "launch: %s", cudaGetErrorString(e)); LM_FAIL(LA_ERR_CUDA); }
@@ -834,7 +890,7 @@ extern "C" {
 
 // perf triage only (not part of the public header): copies the LA_LOGMEL_DBG&8 timestamps out
 int la_debug_logmel_trace(unsigned long long* h_out) {
-    return cudaMemcpyFromSymbol(h_out, la::g_trace, sizeof(unsigned long long) * 4 * 8 * 32) == cudaSuccess ? 0 : -2;
+    return cudaMemcpyFromSymbol(h_out, la::g_trace, sizeof(unsigned long long) * 4 * 8 * la::kTraceEvents) == cudaSuccess ? 0 : -2;
 }
 
 // test hook (not in the public header): the host-built fp16 basis table, so a CPU test can check the slicing

@@ -14,26 +14,31 @@
 // utterance with exactly ceil(pairs / 32K) warps. The dependency runs left to right only, so warps
 // are a PIPELINE, not a lock-step team: warp w hands the score of its last pair to warp w+1
 // through a shared-memory ring of 2 x chunk slots (a 64-bit store; the consumer's lane 0 spins on
-// an all-ones NaN sentinel and re-arms the slot). There is NO block barrier in the frame loop --
-// round 1's per-frame __syncthreads cost 160-250 ns per frame; the barrier is now one per chunk of
-// emission rows, which the staging ring needs anyway.
+// an all-ones NaN sentinel and re-arms the slot). There is NO block barrier in the frame loop
+// (round 1's per-frame __syncthreads cost 160-250 ns per frame) and none per chunk either: the
+// emission stages are recycled through full/empty mbarriers, so the warps never re-align and the
+// pipeline never drains. A single warp is latency-bound on its own instruction stream (~5 cycles per
+// dependent instruction), so the common case -- one pair per lane, eight whole frames inside a chunk --
+// runs an unrolled block whose per-frame work is the dependent chain and nothing else.
 // Emission rows ([T][row_floats], col 0 = blank) are streamed in chunks of up to 32 frames into a
-// 3-deep shared-memory ring by 1-D TMA bulk copies (two chunks in flight: a chunk is consumed in
-// well under a microsecond); the next frame's emissions are read into registers before the
-// current frame's dependent chain starts. Backpointers are 2-bit step codes (k - bt), one nibble
-// per pair per frame, 8 frames per 32-bit word, written coalesced.
+// 3- or 4-deep shared-memory ring by 1-D TMA bulk copies issued by the last warp. Backpointers are
+// 2-bit step codes (k - bt), one nibble per pair per frame, 8 frames per 32-bit word, written coalesced.
 // The backtrace is a single warp walking t = T-1..1: lanes hold a 32-pair window of the current
 // 8-frame block in registers (next block prefetched); the walker takes the current pair's word by
 // shuffle and jumps straight to the next frame whose code is non-zero (count-leading-zeros on the
 // masked word), so its cost is one step per block plus one per transition, not one per frame.
 // Lane 0 emits first / last+1 at every label-state run boundary (the path is monotone, so each
 // label's occupancy is one run).
+#include <cstdlib>
+#include <type_traits>
+
 #include "la_common.cuh"
 
 namespace la {
 
 constexpr int kVitChunkMax = 32;   // frames per TMA chunk (fewer when rows are very wide)
-constexpr int kVitStages = 3;
+constexpr int kVitStagesMax = 4;
+__device__ unsigned long long g_vit_trace[4];   // LA_VIT_TRACE=1: CTA 0's clock64 at DP start / DP end / backtrace end, and T
 constexpr unsigned long long kNotReady = ~0ull;   // all-ones NaN: neither arithmetic nor an f32->f64 promotion can produce it
 
 __device__ __forceinline__ double shfl_up_f64(double v, int delta) {
@@ -42,17 +47,22 @@ __device__ __forceinline__ double shfl_up_f64(double v, int delta) {
     hi = __shfl_up_sync(0xffffffffu, hi, delta);
     return __hiloint2double(hi, lo);
 }
-__device__ __forceinline__ double ring_take(unsigned long long* slot) {
-    const uint32_t a = smem_u32(slot);
+// Hand-off ring (shared-memory byte addresses). take: EVERY lane of the warp polls the same slot (one
+// broadcast LDS, the loop exit is warp-uniform, no divergence); lane 0 then re-arms it. put: a predicated
+// store, no branch. No "memory" clobber: the ring is ordered by `volatile` among these asm statements
+// only, so the compiler stays free to hoist the emission loads above them.
+__device__ __forceinline__ double ring_take(uint32_t addr, uint32_t rearm) {
     unsigned long long v;
     do {
-        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
     } while (v == kNotReady);
-    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(a), "l"(kNotReady) : "memory");   // re-arm
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.volatile.shared.u64 [%0], %1;\n\t}"
+                 ::"r"(addr), "l"(kNotReady), "r"(rearm));
     return __longlong_as_double((long long)v);
 }
-__device__ __forceinline__ void ring_put(unsigned long long* slot, double v) {
-    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(smem_u32(slot)), "l"(__double_as_longlong(v)) : "memory");
+__device__ __forceinline__ void ring_put(uint32_t addr, double v, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.volatile.shared.u64 [%0], %1;\n\t}"
+                 ::"r"(addr), "l"(__double_as_longlong(v)), "r"(pred));
 }
 
 // K = pairs per thread, DUMP = parity instrumentation (full fp64 table to global memory; compiled out of
@@ -63,14 +73,15 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(const VitParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw_launch = blockDim.x >> 5;
 
-    // ---- shared memory carve-up: 3 stages, 3 mbarriers, 2 finals, hand-off ring ----
-    const int chunk = p.chunk;
-    const int ring = 2 * chunk;                           // slots per warp boundary (power of two)
+    // ---- shared memory carve-up: stages, full/empty mbarriers, 2 finals, hand-off ring ----
+    const int chunk = p.chunk, stages = p.stages;
+    const int ring = p.ring;                              // slots per warp boundary (power of two >= stages * chunk)
     const int stage_bytes = chunk * p.row_floats_max * 4;
     float* stage0 = reinterpret_cast<float*>(smem);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kVitStages * stage_bytes);
-    double* fin = reinterpret_cast<double*>(smem + kVitStages * stage_bytes + 32);
-    unsigned long long* xchg = reinterpret_cast<unsigned long long*>(smem + kVitStages * stage_bytes + 64);   // [ring][nw_launch]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);     // [kVitStagesMax]
+    uint64_t* empty = full + kVitStagesMax;                                         // [kVitStagesMax]
+    double* fin = reinterpret_cast<double*>(empty + kVitStagesMax);                 // [2]
+    unsigned long long* xchg = reinterpret_cast<unsigned long long*>(fin + 2);      // [nw_launch][ring]
 
     const int utt = p.order[blockIdx.x];
     const int T = p.m.t_off[utt + 1] - p.m.t_off[utt];
@@ -93,7 +104,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(const VitParams p) {
     if (warp >= nwarps) return;
 
     if (tid == 0) {
-        for (int s = 0; s < kVitStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps); }
         mbar_fence_init();
     }
     for (int i = tid; i < ring * nw_launch; i += 32 * nwarps) xchg[i] = kNotReady;
@@ -103,15 +114,17 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(const VitParams p) {
     auto issue = [&](int c) {
         const int rows = min(chunk, T - c * chunk);
         const uint32_t bytes = (uint32_t)rows * wrow * 4;
-        const int s = c % kVitStages;
+        const int s = c % stages;
         fence_proxy_async();
         mbar_arrive_expect_tx(&full[s], bytes);
         bulk_g2s(reinterpret_cast<unsigned char*>(stage0) + s * stage_bytes, E + (int64_t)c * chunk * wrow, bytes, &full[s]);
     };
-    if (tid == 0) {
-        issue(0);
-        if (nchunks > 1) issue(1);
-    }
+    // The LAST warp refills the stages: it is the pipeline's laggard, so by the time it starts chunk c every
+    // other warp has (all but certainly) left chunk c-1 and the wait on empty[] costs nothing, while the
+    // leading warp -- up to nwarps frames ahead -- still has stages-1 chunks of emissions staged.
+    const bool loader = (warp == nwarps - 1) && lane == 0;
+    if (loader)
+        for (int c = 0; c < min(stages, nchunks); ++c) issue(c);
 
     // ---- per-pair constants ------------------------------------------------------------
     const int pair0 = tid * K;
@@ -127,46 +140,30 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(const VitParams p) {
     uint32_t acc[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) { pb[j] = kFloor; pl[j] = kFloor; acc[j] = 0u; }
-    const bool feeds_right = (lane == 31) && (warp + 1 < nwarps);
-    const bool fed_from_left = (lane == 0) && (warp > 0);
+    const bool has_left = warp > 0;                        // warp-uniform
+    const bool lane0 = lane == 0;
+    uint32_t put_pred = (lane == 31 && warp + 1 < nwarps) ? 1u : 0u;
+    uint32_t rearm = lane0 ? 1u : 0u;
+    uint32_t put_base = smem_u32(xchg) + (uint32_t)(warp * ring) * 8u;          // my slots, read by warp + 1
+    uint32_t take_base = smem_u32(xchg) + (uint32_t)(max(warp, 1) - 1) * ring * 8u;   // the left neighbour's slots
+    const uint32_t ring_mask8 = (uint32_t)(ring - 1) * 8u;
+    // opaque to the optimiser: otherwise ptxas re-derives these from S2R/cvta inside the frame loop
+    asm volatile("" : "+r"(put_pred), "+r"(rearm), "+r"(put_base), "+r"(take_base));
 
-    for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(&full[c % kVitStages], (c / kVitStages) & 1);
-        if (tid == 0 && c + 2 < nchunks) issue(c + 2);    // stage (c+2)%3 was drained in chunk c-1 (barrier below)
-        const float* rows = stage0 + (c % kVitStages) * (stage_bytes / 4);
-        const int t0 = c * chunk;
-        const int nt = min(chunk, T - t0);
-        float fb = rows[0], fl[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) fl[j] = rows[ecol[j]];
-        for (int tt = 0; tt < nt; ++tt) {
-            const int t = t0 + tt;
-            const double eb = (double)fb;
-            double el[K];
-#pragma unroll
-            for (int j = 0; j < K; ++j) el[j] = (double)fl[j];
-            if (tt + 1 < nt) {                             // next frame's emissions: off the dependent chain
-                const float* nr = rows + (tt + 1) * wrow;
-                fb = nr[0];
-#pragma unroll
-                for (int j = 0; j < K; ++j) fl[j] = nr[ecol[j]];
-            }
-            if (t == 0) {
-                // row 0 preset (utils/alignment.py:151-152)
-                if (tid == 0) { pb[0] = eb; pl[0] = el[0]; }
-                if (feeds_right) ring_put(&xchg[warp], pl[K - 1]);
-                if (DUMP) {
-#pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        if (pair0 + j <= L) p.dp_dump[2 * (pair0 + j)] = pb[j];
-                        if (pair0 + j < L) p.dp_dump[2 * (pair0 + j) + 1] = pl[j];
-                    }
-                }
-                continue;
-            }
+    // one frame, any K, every special case checked (frame 0 preset, tail word, DUMP)
+    auto step = [&](int t, double eb, const double (&el)[K]) {
+        if (t == 0) {
+            // row 0 preset (utils/alignment.py:151-152)
+            if (tid == 0) { pb[0] = eb; pl[0] = el[0]; }
+            ring_put(put_base, pl[K - 1], put_pred);
+        } else {
             double ql = shfl_up_f64(pl[K - 1], 1);
-            if (lane == 0) ql = -INFINITY;                 // pair 0: no left neighbour
-            if (fed_from_left) ql = ring_take(&xchg[((t - 1) & (ring - 1)) * nw_launch + warp - 1]);
+            if (has_left) {
+                const double v = ring_take(take_base + (((uint32_t)(t - 1) * 8u) & ring_mask8), rearm);
+                ql = lane0 ? v : ql;
+            } else {
+                ql = lane0 ? -INFINITY : ql;               // pair 0: no left neighbour
+            }
             const int sh = (t & 7) * 4;
 #pragma unroll
             for (int j = 0; j < K; ++j) {
@@ -183,30 +180,97 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(const VitParams p) {
                 const uint32_t nib = (b_stay ? 0u : 1u) | (skip ? 4u : (l_stay ? 0u : 2u));
                 acc[j] |= nib << sh;
             }
-            if (feeds_right) ring_put(&xchg[(t & (ring - 1)) * nw_launch + warp], pl[K - 1]);
-            if (DUMP) {
-                double* drow = p.dp_dump + (int64_t)t * (2 * L + 1);
+            ring_put(put_base + (((uint32_t)t * 8u) & ring_mask8), pl[K - 1], put_pred);
+        }
+        if (DUMP) {
+            double* drow = p.dp_dump + (int64_t)t * (2 * L + 1);
 #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    if (pair0 + j <= L) drow[2 * (pair0 + j)] = pb[j];
-                    if (pair0 + j < L) drow[2 * (pair0 + j) + 1] = pl[j];
-                }
-            }
-            if (sh == 28 || t == T - 1) {
-                uint32_t* w = bp + (int64_t)(t >> 3) * pairs_pad + pair0;
-                if (K == 4) {
-                    *reinterpret_cast<uint4*>(w) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-                } else if (K == 2) {
-                    *reinterpret_cast<uint2*>(w) = make_uint2(acc[0], acc[1]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < K; ++j) w[j] = acc[j];
-                }
-#pragma unroll
-                for (int j = 0; j < K; ++j) acc[j] = 0u;
+            for (int j = 0; j < K; ++j) {
+                if (pair0 + j <= L) drow[2 * (pair0 + j)] = pb[j];
+                if (pair0 + j < L) drow[2 * (pair0 + j) + 1] = pl[j];
             }
         }
-        __syncthreads();                                   // stage fully read before it is refilled; bounds the warps' skew to one chunk
+        if ((t & 7) == 7 || t == T - 1) {
+            uint32_t* w = bp + (int64_t)(t >> 3) * pairs_pad + pair0;
+            if (K == 4) {
+                *reinterpret_cast<uint4*>(w) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            } else if (K == 2) {
+                *reinterpret_cast<uint2*>(w) = make_uint2(acc[0], acc[1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; ++j) w[j] = acc[j];
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) acc[j] = 0u;
+        }
+    };
+    // eight frames t .. t+7 (t a multiple of 8, t >= 8, all inside one chunk), one pair per lane: the
+    // emissions of the whole block are promoted to fp64 up front, shifts and ring offsets are immediates,
+    // and the only per-frame work left is the dependent chain itself
+    auto block8 = [&](int t, const float* r0, auto HL) {
+        constexpr bool kHasLeft = decltype(HL)::value;
+        double ebv[8], elv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            ebv[i] = (double)r0[i * wrow];
+            elv[i] = (double)r0[i * wrow + ecol[0]];
+        }
+        const uint32_t put8 = put_base + (((uint32_t)t * 8u) & ring_mask8);            // slots t .. t+7 are contiguous
+        const uint32_t take0 = take_base + (((uint32_t)(t - 1) * 8u) & ring_mask8);    // slot t-1
+        const uint32_t take8 = take_base + (((uint32_t)t * 8u) & ring_mask8);          // slots t .. t+6 feed frames t+1 .. t+7
+        uint32_t a = 0u;
+        double b = pb[0], l = pl[0];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double q = shfl_up_f64(l, 1);
+            if (kHasLeft) {
+                const double v = ring_take(i == 0 ? take0 : take8 + 8u * (uint32_t)(i - 1), rearm);
+                q = lane0 ? v : q;
+            } else {
+                q = lane0 ? -INFINITY : q;
+            }
+            const bool b_stay = b > q;
+            const bool skip = (q >= b) && (q >= l) && skip_ok[0];
+            const bool l_stay = l > b;
+            const double nb = (b_stay ? b : q) + ebv[i];
+            l = (skip ? q : (l_stay ? l : b)) + elv[i];
+            b = nb;
+            ring_put(put8 + 8u * (uint32_t)i, l, put_pred);
+            a |= ((b_stay ? 0u : 1u) | (skip ? 4u : (l_stay ? 0u : 2u))) << (4 * i);
+        }
+        pb[0] = b; pl[0] = l;
+        bp[(int64_t)(t >> 3) * pairs_pad + pair0] = a;
+    };
+
+    const long long c_fwd0 = clock64();
+    for (int c = 0; c < nchunks; ++c) {
+        const int s = c % stages;
+        if (loader && c >= 1 && c - 1 + stages < nchunks) {
+            mbar_wait(&empty[(c - 1) % stages], ((c - 1) / stages) & 1);   // every warp has left chunk c-1
+            issue(c - 1 + stages);
+        }
+        mbar_wait(&full[s], (c / stages) & 1);
+        const float* rows = stage0 + s * (stage_bytes / 4);
+        const int t0 = c * chunk;
+        const int nt = min(chunk, T - t0);
+        int tt = 0;
+        while (tt < nt) {
+            const int t = t0 + tt;
+            if (K == 1 && !DUMP && (t & 7) == 0 && t >= 8 && tt + 8 <= nt) {
+                if (has_left) block8(t, rows + tt * wrow, std::true_type{});
+                else block8(t, rows + tt * wrow, std::false_type{});
+                tt += 8;
+                continue;
+            }
+            const float* er = rows + tt * wrow;
+            double el[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) el[j] = (double)er[ecol[j]];
+            step(t, (double)er[0], el);
+            ++tt;
+        }
+        __syncwarp();
+        if (lane0) mbar_arrive(&empty[s]);                 // this warp no longer reads stage s
     }
 
     // ---- end-state pick (utils/alignment.py:157): S-1 iff dp[T-1][S-1] > dp[T-1][S-2] --------
@@ -215,50 +279,65 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(const VitParams p) {
         if (pair0 + j == L) fin[0] = pb[j];
         if (pair0 + j == L - 1) fin[1] = pl[j];
     }
-    __syncthreads();                                       // also orders the bp stores of all warps before the walker's loads
+    __syncthreads();                                       // all warps done; also orders their bp stores before the walker's loads
     if (warp != 0) return;
 
+    const long long c_fwd1 = clock64();
     int k = (fin[0] > fin[1]) ? 2 * L : 2 * L - 1;
     const double best = (fin[0] > fin[1]) ? fin[0] : fin[1];
 
-    // ---- backtrace: one warp, window of 32 pairs x 8 frames in registers ----------------------
+    // ---- backtrace: one warp; a tile of 8 blocks (64 frames) x 8 pairs of packed codes in registers ----------
+    // The walker only ever moves to smaller t and smaller k, and an alignment advances about one pair per
+    // tens of frames, so a tile anchored with the current pair at its right edge usually lasts its full 64
+    // frames; the NEXT tile (same 8 pair columns, the 8 blocks before) is requested as soon as the current one
+    // is entered, which hides the ~700-cycle L2 round trip that a one-block look-ahead exposed on every block.
     int32_t* first = p.first + l0;
     int32_t* lastp = p.last_plus1 + l0;
     int visited = 0;
     if ((k & 1) && lane == 0) lastp[k >> 1] = T;
-    auto load_win = [&](int tb, int base) -> uint32_t {
-        const int pr = base + lane;
-        return (tb >= 0 && pr >= 0 && pr < pairs_pad) ? __ldcg(bp + (int64_t)tb * pairs_pad + pr) : 0u;
+    struct Tile { int b0, p0; uint32_t w0, w1; };         // blocks [b0-7, b0], pairs [p0, p0+7]; lane = (b0 - blk) % 4 * 8 + pr - p0
+    auto load_tile = [&](int b0, int p0) -> Tile {
+        const int pr = p0 + (lane & 7);
+        const int blk = b0 - (lane >> 3);
+        const bool ok = pr >= 0 && pr < pairs_pad;
+        Tile tl;
+        tl.b0 = b0; tl.p0 = p0;
+        tl.w0 = (ok && blk >= 0) ? __ldcg(bp + (int64_t)blk * pairs_pad + pr) : 0u;
+        tl.w1 = (ok && blk >= 4) ? __ldcg(bp + (int64_t)(blk - 4) * pairs_pad + pr) : 0u;
+        return tl;
     };
-    int tb = (T - 1) >> 3;
-    int base_cur = (k >> 1) - 31;
-    uint32_t w_cur = load_win(tb, base_cur);
-    while (tb >= 0) {
-        const int base_nxt = (k >> 1) - 31;               // covers the <= 16 pairs the next 2 blocks can reach
-        const uint32_t w_nxt = load_win(tb - 1, base_nxt);
-        const int t_lo = max(1, tb * 8);
-        int t = min(T - 1, tb * 8 + 7);
-        while (t >= t_lo) {
-            // codes of state k over this block: label states use bits 1-2 of each nibble, blank states bit 0
-            const uint32_t word = __shfl_sync(0xffffffffu, w_cur, (k >> 1) - base_cur);
-            uint32_t m = (k & 1) ? (word & 0x66666666u) : (word & 0x11111111u);
-            m &= (0xffffffffu >> (28 - (t & 7) * 4));      // frames above t are already behind the walker
-            m &= ~((1u << ((t_lo & 7) * 4)) - 1u);         // frame 0 carries no code (block 0 only)
-            if (m == 0u) break;                            // state k stays for the rest of the block
-            t = (tb << 3) + ((31 - __clz(m)) >> 2);        // latest frame <= t with a non-zero code
-            const uint32_t nib = (word >> ((t & 7) * 4)) & 0xFu;
-            const int code = (k & 1) ? (int)(nib >> 1) : (int)(nib & 1u);
-            if (k & 1) {                                   // label state k occupied frames t..: onset
-                if (lane == 0) first[k >> 1] = t;
-                ++visited;
-            }
-            k -= code;
-            if ((k & 1) && lane == 0) lastp[k >> 1] = t;   // new label state ends at frame t-1
-            --t;
+    auto covers = [](const Tile& tl, int tb, int pair) {
+        return (unsigned)(tl.b0 - tb) < 8u && (unsigned)(pair - tl.p0) < 8u;
+    };
+    int t = T - 1;
+    Tile cur = load_tile(t >> 3, (k >> 1) - 7);
+    Tile nxt = load_tile((t >> 3) - 8, (k >> 1) - 7);
+    while (t >= 1) {
+        const int tb = t >> 3, pair = k >> 1;
+        if (!covers(cur, tb, pair)) {
+            cur = covers(nxt, tb, pair) ? nxt : load_tile(tb, pair - 7);
+            nxt = load_tile(cur.b0 - 8, pair - 7);
         }
-        w_cur = w_nxt;
-        base_cur = base_nxt;
-        --tb;
+        const int d = cur.b0 - tb;
+        const uint32_t word = __shfl_sync(0xffffffffu, d < 4 ? cur.w0 : cur.w1, (d & 3) * 8 + (pair - cur.p0));
+        // codes of state k over this block: label states use bits 1-2 of each nibble, blank states bit 0
+        uint32_t m = (k & 1) ? (word & 0x66666666u) : (word & 0x11111111u);
+        m &= (0xffffffffu >> (28 - (t & 7) * 4));          // frames above t are already behind the walker
+        if (tb == 0) m &= ~0xFu;                           // frame 0 carries no code
+        if (m == 0u) {                                     // state k stays for the rest of the block
+            t = (tb << 3) - 1;
+            continue;
+        }
+        t = (tb << 3) + ((31 - __clz(m)) >> 2);            // latest frame <= t with a non-zero code
+        const uint32_t nib = (word >> ((t & 7) * 4)) & 0xFu;
+        const int code = (k & 1) ? (int)(nib >> 1) : (int)(nib & 1u);
+        if (k & 1) {                                       // label state k occupied frames t..: onset
+            if (lane == 0) first[k >> 1] = t;
+            ++visited;
+        }
+        k -= code;
+        if ((k & 1) && lane == 0) lastp[k >> 1] = t;       // new label state ends at frame t-1
+        --t;
     }
     if (k & 1) {
         if (lane == 0) first[k >> 1] = 0;
@@ -267,20 +346,33 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(const VitParams p) {
     if (lane == 0) {
         p.status[utt] = (visited == L) ? 0 : 2;          // a missing label state -> ValueError upstream
         p.score[utt] = best;
+        if (p.trace && blockIdx.x == 0) {
+            g_vit_trace[0] = (unsigned long long)(c_fwd0);
+            g_vit_trace[1] = (unsigned long long)(c_fwd1);
+            g_vit_trace[2] = (unsigned long long)clock64();
+            g_vit_trace[3] = (unsigned long long)T;
+        }
     }
 }
 
-// frames per chunk: a power of two (the hand-off ring is indexed with a mask), at most 32, and small
-// enough that three stages of the widest row fit comfortably beside other resident CTAs
+// frames per chunk: a power of two (8-frame blocks and the hand-off ring index with masks), at most 32, and
+// small enough that four stages of the widest row fit in shared memory
 int viterbi_chunk_frames(int row_floats_max) {
     const int fit = (36 * 1024) / (row_floats_max * 4);
     int c = kVitChunkMax;
     while (c > 1 && c > fit) c >>= 1;
     return c;
 }
+// the leading warp runs up to `warps` frames ahead of the last one: give wide utterances one more stage
+static int viterbi_stages(int warps) { return warps > 4 ? 4 : 3; }
+static int viterbi_ring(int chunk, int stages) {
+    int r = 16;
+    while (r < stages * chunk) r <<= 1;
+    return r;
+}
 
-size_t viterbi_smem_bytes(int row_floats_max, int chunk, int warps) {
-    return (size_t)kVitStages * chunk * row_floats_max * 4 + 64 + (size_t)2 * chunk * warps * 8;
+size_t viterbi_smem_bytes(int row_floats_max, int chunk, int stages, int ring, int warps) {
+    return (size_t)stages * chunk * row_floats_max * 4 + 2 * kVitStagesMax * 8 + 16 + (size_t)ring * warps * 8;
 }
 
 template <int K>
@@ -303,9 +395,14 @@ static cudaError_t launch_one(const VitParams& p, int threads, int grid, size_t 
 }
 
 // K pairs per lane; one CTA of `warps` warps per utterance
-cudaError_t launch_viterbi(const VitParams& p, int K, int warps, cudaStream_t stream) {
-    if (p.n_order <= 0) return cudaSuccess;
-    const size_t smem = viterbi_smem_bytes(p.row_floats_max, p.chunk, warps);
+cudaError_t launch_viterbi(const VitParams& p_in, int K, int warps, cudaStream_t stream) {
+    if (p_in.n_order <= 0) return cudaSuccess;
+    VitParams p = p_in;
+    static const int trace = [] { const char* e = getenv("LA_VIT_TRACE"); return e ? atoi(e) : 0; }();
+    p.trace = trace;
+    p.stages = viterbi_stages(warps);
+    p.ring = viterbi_ring(p.chunk, p.stages);
+    const size_t smem = viterbi_smem_bytes(p.row_floats_max, p.chunk, p.stages, p.ring, warps);
     switch (K) {
         case 1: return launch_one<1>(p, 32 * warps, p.n_order, smem, stream);
         case 2: return launch_one<2>(p, 32 * warps, p.n_order, smem, stream);
@@ -315,3 +412,8 @@ cudaError_t launch_viterbi(const VitParams& p, int K, int warps, cudaStream_t st
 }
 
 }  // namespace la
+
+// perf triage only (not part of the public header)
+extern "C" int la_debug_viterbi_trace(unsigned long long* h_out) {
+    return cudaMemcpyFromSymbol(h_out, la::g_vit_trace, sizeof(unsigned long long) * 4) == cudaSuccess ? 0 : -2;
+}

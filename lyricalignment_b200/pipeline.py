@@ -7,10 +7,10 @@ plain PyTorch modules here -- ``transformers``' WhisperEncoder with random weigh
 ``RNN`` (module/align_model.py:11-40). What this module adds is the framing arithmetic of the
 reference around them, on the device:
 
-  * audios zero-padded to the batch maximum (align_model.py:78-82), ONE log-mel call with the global
-    max (K1, :84),
-  * <= 3000 mel frames: T = int(round(F / 2.0)) (half-to-even), mel zero-padded to the 30 s window,
-    encoder on the full window, output sliced to T (:87-92),
+  * audios zero-padded to the batch maximum ON THE DEVICE (align_model.py:78-82), ONE log-mel call with the
+    global max (K1, :84) written directly into the zero-padded encoder window(s),
+  * <= 3000 mel frames: T = int(round(F / 2.0)) (half-to-even), encoder on the full 30 s window, output
+    sliced to T (:87-92),
   * > 3000 frames: independent 3000-frame chunks, each sliced to round(len / 2), concatenated (:93-104),
   * head over the concatenated embedding -> logits [B, T, V] on the device, ready for
     ``perform_viterbi_ctc`` without the ``.cpu()`` round trip.
@@ -26,6 +26,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from . import _lib
 from . import audio as LA
 
 WHISPER_DIMS = {"tiny": (384, 4, 6), "base": (512, 6, 8), "small": (768, 12, 12),
@@ -72,20 +73,36 @@ class AlignPipeline(nn.Module):
 
     @torch.no_grad()
     def frame_manual_forward(self, audios: Sequence[np.ndarray]) -> torch.Tensor:
-        n = max(len(a) for a in audios)
-        batch = np.zeros((len(audios), n), np.float32)                 # align_model.py:78-82
-        for i, a in enumerate(audios):
-            batch[i, :len(a)] = a
-        mel = LA.log_mel_spectrogram(batch, device=self.device)        # K1, global max (:84)
-        F_ = mel.shape[-1]
+        """module/align_model.py:72-123 with every byte of the framing on the device:
+        one pinned concat + ONE H2D of the ragged clips, the zero-padded [B, n_max] batch built by a single
+        masked scatter (align_model.py:78-82 does it with np.append per item on the host), and K1 writing the
+        log-mel straight into a pre-zeroed [B, 80, 3000 * n_chunks] tensor -- which IS the pad_or_trim'ed
+        encoder window of every chunk (align_model.py:89,100; 0.0 is the pad value in normalised log-mel
+        units), so no pad_or_trim copy is made."""
+        lib = _lib.load()
+        dev = self.device
+        lens = np.fromiter((len(a) for a in audios), dtype=np.int64, count=len(audios))
+        B, n = len(audios), int(lens.max())
+        flat = torch.from_numpy(np.concatenate([np.asarray(a, dtype=np.float32).reshape(-1) for a in audios]))
+        flat = flat.pin_memory().to(dev, non_blocking=True)
+        lens_d = torch.from_numpy(lens).to(dev, non_blocking=True)
+        n_pad = (n + 3) // 4 * 4                                        # rows 16-byte aligned -> K1's TMA path
+        batch = torch.zeros((B, n_pad), dtype=torch.float32, device=dev)
+        batch[torch.arange(n_pad, device=dev)[None, :] < lens_d[:, None]] = flat      # align_model.py:78-82
+        F_ = n // LA.HOP_LENGTH
+        n_chunks = max(1, -(-F_ // LA.N_FRAMES))
+        mel = torch.zeros((B, LA.N_MELS, LA.N_FRAMES * n_chunks), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = torch.empty(int(lib.la_logmel_workspace_bytes(B, B * n)), dtype=torch.uint8, device=dev)
+            _lib.check(lib.la_logmel(batch.data_ptr(), B, n, n_pad, mel.data_ptr(), mel.shape[-1], ws.data_ptr(),
+                                     torch.cuda.current_stream(dev).cuda_stream), "la_logmel")   # K1, global max (:84)
         if F_ <= LA.N_FRAMES:
             T = LA.decode_frames(F_)                                   # :88
-            embed = self.embed_audio(LA.pad_or_trim(mel, LA.N_FRAMES))[:, :T, :]
+            embed = self.embed_audio(mel)[:, :T, :]
         else:
             parts = []
             for s in range(0, F_, LA.N_FRAMES):                        # :95-104
                 e = min(s + LA.N_FRAMES, F_)
-                cur = LA.pad_or_trim(mel[:, :, s:e], LA.N_FRAMES)
-                parts.append(self.embed_audio(cur)[:, :LA.decode_frames(e - s), :])
+                parts.append(self.embed_audio(mel[:, :, s:s + LA.N_FRAMES])[:, :LA.decode_frames(e - s), :])
             embed = torch.cat(parts, dim=1)
         return self.head(embed)                                        # [B, T, V] on the device

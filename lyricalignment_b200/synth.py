@@ -47,6 +47,21 @@ def opencpop_shaped(n_clips: int, seed: int = 114514, dmin: float = 5.0, dmax: f
     return ClipBatch(d, n, t, labels)
 
 
+def fresh_labels(batch: ClipBatch, seed: int) -> List[np.ndarray]:
+    """New lyrics for the SAME clips (same durations / frame counts): what a recycled logits pool is aligned
+    against in the 10^6-clip run. Vectorised: 2 000 clips in well under a millisecond."""
+    rng = np.random.default_rng(seed)
+    n = len(batch.t_len)
+    L = np.clip(np.rint(2.4 * batch.durations * rng.uniform(0.7, 1.3, size=n)), 1, np.maximum(1, batch.t_len // 2)).astype(np.int64)
+    ids = rng.integers(2, N_CLASSES + 1, size=int(L.sum()))
+    rep = rng.random(ids.size) < 0.05
+    starts = np.concatenate([[0], np.cumsum(L)[:-1]])
+    rep[starts] = False
+    idx = np.nonzero(rep)[0]
+    ids[idx] = ids[idx - 1]                                # 5 % repeats of the previous syllable (chains are rare; good enough)
+    return np.split(ids.astype(np.int64), np.cumsum(L)[:-1])
+
+
 def planted_logits(batch: ClipBatch, V: int = V_HEAD, ctc: bool = True, device="cuda", seed: int = 114514,
                    scale: float = 2.0, boost: float = 8.0) -> torch.Tensor:
     """[sum T, V] fp32 logits: randn * scale, +boost on the true label column along a random

@@ -1,4 +1,8 @@
-"""Timeline of CTA 0's first tiles in K1 (LA_LOGMEL_DBG=8). Perf triage only."""
+"""Timeline of CTA 0's first tiles in K1 (LA_LOGMEL_DBG=8). Perf triage only.
+Events (la_logmel.cu `trace`): role 0 = cross-term MMA issuer: 0/29 TMEM free pass 0/1, 1+i operands of
+k-step i ready (i = 0..25), 27/28 pass 0/1 committed; role 1 = transform warp 12: 0 raw_full, 1 scale known,
+2+j its j-th k-step's TMEM stage free, 30 tile done; role 2 = epilogue warp 4: 0/2 tmem_full pass 0/1,
+1/3 drained pass 0/1, 4 finish done; role 3 = producer: 0 raw_empty ok, 1 raw issued, 2+i basis stage free."""
 import ctypes, os, sys
 os.environ["LA_LOGMEL_DBG"] = os.environ.get("LA_LOGMEL_DBG", "8")
 import numpy as np, torch
@@ -10,23 +14,20 @@ wave, off = synth.synthetic_waveforms(batch, device="cuda")
 for _ in range(3):
     LA.log_mel_spectrogram_ragged(wave, off, batch.n_samples.astype(np.int32))
 torch.cuda.synchronize()
-buf = (ctypes.c_ulonglong * (4 * 8 * 32))()
+buf = (ctypes.c_ulonglong * (4 * 8 * 64))()
 lib.la_debug_logmel_trace.argtypes = [ctypes.c_void_p]
 assert lib.la_debug_logmel_trace(buf) == 0
-t = np.array(buf, dtype=np.int64).reshape(4, 8, 32)
+t = np.array(buf, dtype=np.int64).reshape(4, 8, 64)
 t0 = t[t > 0].min()
-names = ["mma", "xform", "epi", "prod"]
 for tl in range(1, 6):
-    print(f"--- tile {tl} (ns since first event)")
     m, x, e, p = t[0, tl] - t0, t[1, tl] - t0, t[2, tl] - t0, t[3, tl] - t0
-    print(f" prod: raw_empty ok {p[0]}, raw issued {p[1]}, empty-wait ok ks0..4 {p[2:7].tolist()} ... ks24 {p[26]}")
-    print(f" xform: raw_full ok {x[0]}, empty ok ks0..4 {x[1:6].tolist()} ... ks24 {x[25]}, done {x[26]}")
-    print(f" mma: tmem_empty ok {m[0]}, full ok ks0..4 {m[1:6].tolist()} ... ks24 {m[25]}, committed {m[26]}")
-    print(f" epi: tmem_full ok {e[0]}, w4 chunks done {e[2]}, w4 flushed {e[3]}, barrier passed {e[4]}, end {e[1]} | w8 chunks done {e[5]}, w8 flushed {e[6]}")
-    print(f" xform first k-step: raw_full {x[0]}, edges staged {x[27]}, computed {x[28]}, stage free {x[1]}, stored {x[29]}, arrived {x[30]}")
-    print(f" per-kstep mma deltas (ns): {np.diff(m[1:26]).tolist()}")
-tl = 3
-m, x, p = t[0, tl] - t0, t[1, tl] - t0, t[3, tl] - t0
-print("ks : mma full-ok | xform(a_empty ok, even ks only) | producer b_empty ok")
-for ks in range(25):
-    print(f"{ks:2d} : {m[1+ks]:7d} | {x[1+ks] if ks % 2 == 0 else -1:7d} | {p[2+ks]:7d}")
+    print(f"--- tile {tl} (ns since first event); tile period {t[0, tl, 0] - t[0, tl - 1, 0]} ns")
+    print(f" prod : raw_empty ok {p[0]}, raw issued {p[1]}, basis stage free k0..3 {p[2:6].tolist()} .. k25 {p[27]}")
+    print(f" xform: raw_full ok {x[0]}, scanned {x[31]}, barrier passed {x[29]}, scale known {x[1]}, tile done {x[30]}")
+    print(f"        own k-steps computed {x[16:23].tolist()}")
+    print(f"        own stages free      {x[2:9].tolist()}")
+    print(f" mma  : pass0 TMEM free {m[0]}, pass0 committed {m[27]} | pass1 TMEM free {m[29]}, pass1 committed {m[28]}")
+    print(f" epi  : pass0 full {e[0]} drained {e[1]} | pass1 full {e[2]} drained {e[3]} finish done {e[4]}")
+    print(f" issuer k-steps 4..7: [start, 4 MMAs issued, look-ahead done, 5th issued, committed] relative to k4 start:")
+    for j in range(4):
+        print(f"        k{4+j}: {(m[32+5*j:37+5*j] - m[32]).tolist()}")

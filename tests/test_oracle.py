@@ -6,7 +6,11 @@ import numpy as np
 import pytest
 
 import oracle
+import sys
+
 from conftest import GOLDEN, split_onoff
+
+GOLDEN_DIR = GOLDEN
 
 
 def _labels_rows(labels):
@@ -172,3 +176,51 @@ def test_generated_mel_table_matches_oracle_filterbank():
     ms = int(re.search(r"#define LA_MEL_MS (\d+)", txt).group(1))
     split = int(re.search(r"#define LA_MEL_SPLIT (\d+)", txt).group(1))
     assert ms == int(rows[split][1])
+
+
+@pytest.mark.parametrize("name", ["c1_30s", "c4_300s"])
+def test_logmel_oracle_pinned_to_two_independent_implementations(name):
+    """openai-whisper is absent, so the log-mel oracle is a restatement. Pin it on the benchmark shapes
+    (30 s clip, 5-minute song) to the two implementations of the same algorithm this image has
+    (tests/golden/make_logmel_golden.py): HF's numpy extractor (fp64 inside; must agree to fp32 storage
+    precision) and HF's torch.stft fp32 extractor (whisper's own formulation; agrees to fp32-FFT accuracy)."""
+    sys.path.insert(0, GOLDEN_DIR)
+    from make_logmel_golden import signal
+    g = np.load(os.path.join(GOLDEN_DIR, "logmel_hf_long.npz"))
+    stride = int(g[f"{name}/stride"])
+    got = oracle.log_mel_spectrogram(signal(name))[:, ::stride]
+    e_np = 4.0 * np.abs(got - g[f"{name}/hf_numpy"])                # log10 units
+    e_t = 4.0 * np.abs(got - g[f"{name}/hf_torch_f32"])
+    assert e_np.max() <= 1e-6, float(e_np.max())
+    assert e_t.max() <= 2e-4 and np.quantile(e_t, 0.9999) <= 1e-5, (float(e_t.max()), float(np.quantile(e_t, 0.9999)))
+
+
+def test_k1_basis_table_slices_sum_to_the_windowed_dft_basis():
+    """Host logic of K1 (no GPU): the fp16 operand slices la_logmel.cu builds for the tensor cores.
+    B1 must lie on the 64-grid with |B1| <= 2^14 (that is what makes the Acc0 chain exact in fp32), and
+    B1 + B2 + B3 must reproduce 2^14 w[n] cos|(-sin)(2 pi k n / 400) to 2^-30 of full scale."""
+    import ctypes
+    from lyricalignment_b200 import _lib
+    lib = _lib.load()
+    lib.la_debug_logmel_basis.restype = ctypes.c_size_t
+    lib.la_debug_logmel_basis.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    n = lib.la_debug_logmel_basis(None, 0)
+    assert n == 26 * 3 * 3328
+    buf = np.zeros(n, np.uint16)
+    lib.la_debug_logmel_basis(buf.ctypes.data, n)
+    blocks = buf.view(np.float16).astype(np.float64).reshape(2, 13, 3, 2, 26, 8, 8)   # [pass][ks][slice][ki][ni][bin%8][kk%8]
+    B = blocks.transpose(0, 2, 1, 3, 6, 4, 5).reshape(2, 3, 208, 208)                 # [pass][slice][n = 16ks + 8ki + kk][bin]
+    nn = np.arange(208)
+    w = np.where((nn >= 1) & (nn <= 200), 0.5 - 0.5 * np.cos(2 * np.pi * nn / 400.0), 0.0)
+    ph = np.outer(nn, np.arange(208)) % 400
+    C = w[:, None] * np.cos(2 * np.pi * ph / 400.0)
+    S = -w[:, None] * np.sin(2 * np.pi * ph / 400.0)
+    C[200] *= 0.5
+    S[200] = 0.0
+    C[:, 201:] = 0.0
+    S[:, 201:] = 0.0
+    for pas, want in ((0, C), (1, S)):
+        b1, b2, b3 = B[pas]
+        assert np.all(b1 % 64 == 0) and np.abs(b1).max() <= 16384
+        assert np.abs(b2).max() <= 32.0 and np.abs(b3).max() <= 2.0 ** -6
+        assert np.abs(b1 + b2 + b3 - 16384.0 * want).max() <= 2.0 ** -16      # 2^-30 of full scale
