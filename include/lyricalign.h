@@ -129,6 +129,28 @@ int la_align(const la_plan* plan, const float* d_logits, int64_t ld, void* d_wor
              int32_t* d_first, int32_t* d_last_plus1, double* d_score, int32_t* d_status,
              void* stream);
 
+/* ---- N1: the head's Linear fused with K2 (device buffers) -------------------------------------
+ * Replaces the producer AND the consumer of the [T][V] logits: `self.fc(self.activate(out))`
+ * (module/align_model.py:32-33,38,107) and the emission math (utils/alignment.py:123-134 / :14-20). The caller
+ * passes the Mish output d_X float32 [sum T][D] (row stride ldx; D a multiple of 32, <= 1024; 768 in the
+ * reference), the Linear's weight d_W float32 [V][D] (row stride ldw) and bias d_bias [V]; the logits are never
+ * materialised. la_head_pack_weights() converts the weight once per model into the tensor-core layout
+ * (la_head_packed_weight_bytes(V, D) bytes of device memory, caller-owned). la_head_emit() fills the plan's
+ * emission rows exactly as la_emit() does (so la_viterbi() follows); d_head_ws needs
+ * la_head_workspace_bytes(plan, D) bytes. The normaliser is computed on the tensor cores from fp16 hi/lo slices
+ * (|x|, |w| < 65504), the gathered label logits in plain fp32; emissions agree with the fp64 evaluation of
+ * X W^T + b to 1e-4 (la_emit on materialised fp32 logits: 2e-5). */
+size_t la_head_packed_weight_bytes(int V, int D);
+int la_head_pack_weights(const float* d_W, int64_t ldw, int V, int D, void* d_packed, void* stream);
+size_t la_head_workspace_bytes(const la_plan* plan, int D);
+int la_head_emit(const la_plan* plan, const float* d_X, int64_t ldx, int D, const float* d_W, int64_t ldw,
+                 const float* d_bias, const void* d_packed_w, void* d_head_workspace, void* d_workspace,
+                 void* stream);
+/* la_head_emit + la_viterbi */
+int la_head_align(const la_plan* plan, const float* d_X, int64_t ldx, int D, const float* d_W, int64_t ldw,
+                  const float* d_bias, const void* d_packed_w, void* d_head_workspace, void* d_workspace,
+                  int32_t* d_first, int32_t* d_last_plus1, double* d_score, int32_t* d_status, void* stream);
+
 /* ---- same, HOST buffers (the reference's actual call: logits already `.cpu()`ed,
  * inference_alignment.py:161-166). Streams the logits through a double-buffered device
  * staging area owned by a per-device library context (grown on first use and reused across

@@ -33,6 +33,11 @@ SIGNATURES = {
     "la_viterbi_debug": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "la_align": (_c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "la_align_host": (_c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz]),
+    "la_head_packed_weight_bytes": (_sz, [_c_int, _c_int]),
+    "la_head_pack_weights": (_c_int, [_vp, _i64, _c_int, _c_int, _vp, _vp]),
+    "la_head_workspace_bytes": (_sz, [_vp, _c_int]),
+    "la_head_emit": (_c_int, [_vp, _vp, _i64, _c_int, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "la_head_align": (_c_int, [_vp, _vp, _i64, _c_int, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "la_logmel_workspace_bytes": (_sz, [_c_int, _i64]),
     "la_logmel": (_c_int, [_vp, _c_int, _i64, _i64, _vp, _i64, _vp, _vp]),
     "la_logmel_ragged": (_c_int, [_vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 SO_PATH = os.path.join(OUT_DIR, "liblyricalign.so")
-SOURCES = ["la_emit.cu", "la_viterbi.cu", "la_logmel.cu", "la_api.cu"]
+SOURCES = ["la_emit.cu", "la_viterbi.cu", "la_logmel.cu", "la_head.cu", "la_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

@@ -403,6 +403,75 @@ int la_align(const la_plan* P, const float* d_logits, int64_t ld, void* d_ws, in
     return la_viterbi(P, d_ws, d_first, d_last, d_score, d_status, stream);
 }
 
+// ---- N1: fused head (Linear + log-softmax + gather) ------------------------------------------
+static inline bool head_dim_ok(int D) { return D >= 32 && D <= 1024 && D % 32 == 0; }
+
+size_t la_head_packed_weight_bytes(int V, int D) {
+    if (V <= 0 || !head_dim_ok(D)) return 0;
+    return la::head_packed_bytes(V, D, true);
+}
+
+int la_head_pack_weights(const float* d_W, int64_t ldw, int V, int D, void* d_packed, void* stream) {
+    if (!d_W || !d_packed) return fail(LA_ERR_ARG, "null argument");
+    if (V <= 0 || !head_dim_ok(D)) return fail(LA_ERR_ARG, "D must be a multiple of 32 in [32, 1024]");
+    if (ldw < D || (ldw & 3) || (reinterpret_cast<uintptr_t>(d_W) & 15)) return fail(LA_ERR_ARG, "weight rows must be 16-byte aligned");
+    LA_CUDA(la::launch_head_pack(d_W, ldw, V, D, d_packed, true, static_cast<cudaStream_t>(stream)));
+    return LA_OK;
+}
+
+size_t la_head_workspace_bytes(const la_plan* P, int D) {
+    if (!P || !head_dim_ok(D)) return 0;
+    return align_up(la::head_packed_bytes(P->total_T, D, false), 256) + align_up((size_t)std::max<int64_t>(P->total_T, 1) * 8, 256);
+}
+
+int la_head_emit(const la_plan* P, const float* d_X, int64_t ldx, int D, const float* d_W, int64_t ldw,
+                 const float* d_bias, const void* d_packed_w, void* d_head_ws, void* d_ws, void* stream) {
+    if (!P || !d_ws) return fail(LA_ERR_ARG, "null argument");
+    if (P->mode != LA_MODE_CTC && P->mode != LA_MODE_CE) return fail(LA_ERR_ARG, "la_head_emit needs LA_MODE_CTC or LA_MODE_CE");
+    if (P->total_T == 0) return LA_OK;
+    if (!d_X || !d_W || !d_bias || !d_packed_w || !d_head_ws) return fail(LA_ERR_ARG, "null argument");
+    if (!head_dim_ok(D)) return fail(LA_ERR_ARG, "D must be a multiple of 32 in [32, 1024]");
+    if (ldx < D || (ldx & 3) || (reinterpret_cast<uintptr_t>(d_X) & 15)) return fail(LA_ERR_ARG, "activation rows must be 16-byte aligned");
+    if (ldw < D) return fail(LA_ERR_ARG, "weight row stride smaller than D");
+    LA_CUDA(cudaSetDevice(P->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char* hw = static_cast<unsigned char*>(d_head_ws);
+    const size_t xp_bytes = align_up(la::head_packed_bytes(P->total_T, D, false), 256);
+    LA_CUDA(la::launch_head_pack(d_X, ldx, P->total_T, D, hw, false, st));
+    la::HeadParams hp;
+    hp.xp = hw;
+    hp.wp = static_cast<const unsigned char*>(d_packed_w);
+    hp.bias = d_bias;
+    hp.lse = reinterpret_cast<float2*>(hw + xp_bytes);
+    hp.rows = (int)P->total_T;
+    hp.m_tiles = (int)((P->total_T + la::head_tile_rows() - 1) / la::head_tile_rows());
+    hp.n_tiles = (P->V + la::head_tile_cols() - 1) / la::head_tile_cols();
+    hp.ksteps = D / 16;
+    hp.V = P->V;
+    hp.col_lo = P->mode == LA_MODE_CTC ? 1 : 0;            // utils/alignment.py:123: softmax over [:, :, 1:-1]
+    hp.col_hi = P->mode == LA_MODE_CTC ? P->V - 2 : P->V - 1;
+    LA_CUDA(la::launch_head_lse(hp, P->sm_count, st));
+    la::HeadGatherParams gp;
+    gp.m = P->meta;
+    gp.X = d_X; gp.ldx = ldx; gp.W = d_W; gp.ldw = ldw; gp.bias = d_bias;
+    gp.lse = hp.lse;
+    gp.E = static_cast<float*>(d_ws);
+    gp.rows = P->total_T;
+    gp.D = D;
+    LA_CUDA(la::launch_head_gather(gp, st));
+    P->last_stream = st;
+    P->used = true;
+    return LA_OK;
+}
+
+int la_head_align(const la_plan* P, const float* d_X, int64_t ldx, int D, const float* d_W, int64_t ldw,
+                  const float* d_bias, const void* d_packed_w, void* d_head_ws, void* d_ws, int32_t* d_first,
+                  int32_t* d_last, double* d_score, int32_t* d_status, void* stream) {
+    int rc = la_head_emit(P, d_X, ldx, D, d_W, ldw, d_bias, d_packed_w, d_head_ws, d_ws, stream);
+    if (rc) return rc;
+    return la_viterbi(P, d_ws, d_first, d_last, d_score, d_status, stream);
+}
+
 static int grow(void** p, size_t* have, size_t need) {
     if (*have >= need) return LA_OK;
     if (*p) cudaFree(*p);

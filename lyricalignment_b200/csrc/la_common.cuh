@@ -121,6 +121,33 @@ struct VitParams {
     double* dp_dump;        // debug/parity only: full fp64 table [T][2L+1] of a 1-utterance plan, or null
 };
 
+// N1 (la_head.cu): fused head Linear + log-sum-exp + label gather
+struct HeadParams {
+    const unsigned char* xp;   // packed activations [row tiles][k-steps][A_hi | A_lo]
+    const unsigned char* wp;   // packed weights     [col tiles][k-steps][B_hi | B_lo]
+    const float* bias;         // [V]
+    float2* lse;               // [rows]: (max, sum exp(z - max)) over the softmax columns [col_lo, col_hi]
+    int rows, m_tiles, n_tiles, ksteps, V, col_lo, col_hi;
+};
+struct HeadGatherParams {
+    BatchMeta m;
+    const float* X;            // [rows][D] activations (the Mish output)
+    int64_t ldx;
+    const float* W;            // [V][D] the Linear's weight
+    int64_t ldw;
+    const float* bias;         // [V]
+    const float2* lse;         // from head_lse_kernel
+    float* E;                  // the plan's emission area (same layout K2 writes)
+    int64_t rows;
+    int D;
+};
+size_t head_packed_bytes(int64_t rows, int D, bool weights);
+int head_tile_rows();
+int head_tile_cols();
+cudaError_t launch_head_pack(const float* src, int64_t ld, int64_t rows, int D, void* dst, bool weights, cudaStream_t stream);
+cudaError_t launch_head_lse(const HeadParams& p, int sm_count, cudaStream_t stream);
+cudaError_t launch_head_gather(const HeadGatherParams& g, cudaStream_t stream);
+
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
 cudaError_t launch_viterbi(const VitParams& p, int K, int warps, cudaStream_t stream);
 int viterbi_chunk_frames(int row_floats_max);

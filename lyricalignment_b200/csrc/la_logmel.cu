@@ -247,6 +247,13 @@ __device__ __forceinline__ RawPlan raw_plan(const ClipDesc& c, int j0, int f0) {
     return r;
 }
 
+// mel power -> (log10(max(v, 1e-10)) + 4) / 4 as ONE SFU op + ONE FFMA: log10(v) / 4 = lg2(v) * (log10(2) / 4). The accurate
+// log10f is ~25 instructions; 40 of them per thread in the finish phase saturated the schedulers exactly while the
+// transform warps were computing the next tile's scale (3-4 us per tile). lg2.approx is within 2^-22 absolute,
+// i.e. 1e-8 of the output, four orders below the 2.5e-5 budget.
+__device__ __forceinline__ float mel_to_y(float v) {
+    return fmaf(__log2f(fmaxf(v, 1e-10f)), 0.07525749891599529f, 1.0f);
+}
 __device__ __forceinline__ float max4abs(const float4 v, float m) {
     return fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fmaxf(fabsf(v.y), fabsf(v.z)), fabsf(v.w)));
 }
@@ -437,17 +444,25 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 for (int g = 0; g < rp.need; ++g) {
                     if (g >= rp.lo && g < rp.hi) continue;
                     const int cnt = min(kRawGroup, kRawRows - g * kRawGroup) * kHop;
-                    for (int i = xt; i < cnt; i += 512) {
+                    float v[3];                                     // <= 1280 samples per group: all three loads in flight at once
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int i = xt + 512 * u;
                         int j = j0 + g * kRawGroup * kHop + i;
                         if (j < 0) j = -j;
                         if (j >= N) j = 2 * (N - 1) - j;
                         j = j < 0 ? 0 : (j >= N ? N - 1 : j);
-                        const float v = __ldg(x + j);
-                        raw[g * kRawGroupPitch + i] = v;
-                        m = fmaxf(m, fabsf(v));
+                        v[u] = i < cnt ? __ldg(x + j) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int i = xt + 512 * u;
+                        if (i < cnt) raw[g * kRawGroupPitch + i] = v[u];
+                        m = fmaxf(m, fabsf(v[u]));
                     }
                 }
             }
+            if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 32);
             {
                 // the TMA-staged groups [lo, hi) are one contiguous range of the staging buffer (the 8-float pads
                 // between groups and the unused tail of the last group were zeroed once at kernel start and are
@@ -456,6 +471,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
                 const int i1 = ((p.dbg & 256) ? rp.lo : rp.hi) * (kRawGroupPitch / 4);
                 for (int i = rp.lo * (kRawGroupPitch / 4) + xt; i < i1; i += 512) m = max4abs(src[i], m);
             }
+            if (warp == 12 && lane == 0) trace(p.dbg, 1, tl, 33);
 #pragma unroll
             for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (lane == 0) wmax[(tl & 1) * 16 + (warp - 12)] = m;
@@ -650,7 +666,7 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
 #pragma unroll 8
                     for (int m = 0; m < kMels / 2; ++m, src += kTileM, dst += c.out_stride) {
                         const float v = *src * sc2;
-                        *dst = (log10f(fmaxf(v, 1e-10f)) + 4.0f) / 4.0f;
+                        *dst = mel_to_y(v);
                         mx = fmaxf(mx, v);
                         mn = fminf(mn, v);
                     }
@@ -684,9 +700,8 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel_kernel(const LogmelP
 __global__ void logmel_floor_kernel(const LogmelParams p) {
     const int tile = blockIdx.x;
     const ClipDesc c = p.clips[p.tile_clip[tile]];
-    const float gmax = log10f(fmaxf(__int_as_float(p.group_max[c.group]), 1e-10f));
-    const float floor_y = ((gmax - 8.0f) + 4.0f) / 4.0f;
-    const float min_y = (log10f(fmaxf(__int_as_float(p.tile_min[tile]), 1e-10f)) + 4.0f) / 4.0f;
+    const float floor_y = mel_to_y(__int_as_float(p.group_max[c.group])) - 2.0f;    // (x - 8 + 4) / 4 == (x + 4) / 4 - 2
+    const float min_y = mel_to_y(__int_as_float(p.tile_min[tile]));
     if (min_y >= floor_y) return;
     const int f = (tile - c.tile0) * kTileM + threadIdx.x;     // one frame column per thread, coalesced along f
     if (f >= c.n_frames) return;

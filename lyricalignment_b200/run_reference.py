@@ -12,8 +12,9 @@ imports are re-pointed:
 
 (`from utils.alignment import ...` in inference_alignment.py:22 and `from whisper.audio import ...`
 in module/align_model.py:9 then bind the CUDA versions.) The scripts' `align_logits.cpu()` keeps
-working -- host logits are streamed back through the library's double-buffered host path; set
-LA_KEEP_LOGITS_ON_GPU=1 to make `.cpu()` a no-op on the align logits' way to the decoder.
+working -- host logits are streamed back through the library's double-buffered host path (PCIe-bound);
+deleting that one line (inference_alignment.py:161, inference_alignment_nogt.py:156) keeps the logits on
+the GPU and is the only edit worth making.
 """
 from __future__ import annotations
 

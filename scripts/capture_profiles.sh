@@ -5,7 +5,7 @@ set -x
 mkdir -p gpurun_out
 # only the product's kernels (the synthetic-input generation launches hundreds of torch kernels first)
 ncu --metrics gpu__time_duration.sum --clock-control none \
-    -k regex:"emit_kernel|viterbi_kernel|logmel_kernel|logmel_finalize_kernel|fill_int_kernel|gather_logp_kernel" \
+    -k regex:"emit_kernel|viterbi_kernel|logmel_kernel|logmel_floor_kernel|logmel_init_kernel|gather_logp_kernel" \
     -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --skip-e2e > gpurun_out/launches_bench.log 2>&1
 for k in emit_kernel logmel_kernel viterbi_kernel; do

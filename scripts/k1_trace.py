@@ -23,7 +23,7 @@ for tl in range(1, 6):
     m, x, e, p = t[0, tl] - t0, t[1, tl] - t0, t[2, tl] - t0, t[3, tl] - t0
     print(f"--- tile {tl} (ns since first event); tile period {t[0, tl, 0] - t[0, tl - 1, 0]} ns")
     print(f" prod : raw_empty ok {p[0]}, raw issued {p[1]}, basis stage free k0..3 {p[2:6].tolist()} .. k25 {p[27]}")
-    print(f" xform: raw_full ok {x[0]}, scanned {x[31]}, barrier passed {x[29]}, scale known {x[1]}, tile done {x[30]}")
+    print(f" xform: raw_full ok {x[0]}, edges done {x[32]}, scan loop done {x[33]}, scanned {x[31]}, barrier passed {x[29]}, scale known {x[1]}, tile done {x[30]}")
     print(f"        own k-steps computed {x[16:23].tolist()}")
     print(f"        own stages free      {x[2:9].tolist()}")
     print(f" mma  : pass0 TMEM free {m[0]}, pass0 committed {m[27]} | pass1 TMEM free {m[29]}, pass1 committed {m[28]}")

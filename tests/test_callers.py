@@ -92,3 +92,43 @@ def test_io_schema_roundtrip(tmp_path):
     assert back[0].lyric_onset_offset == pred[0] and back[1].text == "好"
     with pytest.raises(AssertionError):
         lio.read_data(str(tmp_path / "missing.json"))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/inference_alignment.py"), reason="reference tree not mounted")
+def test_runner_repoints_the_real_entry_scripts_import_graph(monkeypatch):
+    """run_reference.install() against the REAL inference_alignment.py / inference_alignment_nogt.py: their whole
+    import graph (module.align_model, dataset, utils.audio, ...) is imported with the packages this image lacks
+    (whisper, librosa, pypinyin) stubbed, and the names the scripts bound at import time must be the CUDA ones."""
+    import importlib
+    import types
+    for m in [k for k in sys.modules if k.split(".")[0] in ("utils", "module", "dataset", "data_processor", "whisper",
+                                                             "librosa", "inference_alignment", "inference_alignment_nogt")]:
+        monkeypatch.delitem(sys.modules, m)
+    monkeypatch.setattr(sys, "path", ["/root/reference"] + list(sys.path))
+
+    import importlib.machinery
+    import transformers  # noqa: F401  (its lazy-module probes for optional packages must run before the stubs exist)
+
+    def stub(name, **attrs):
+        mod = types.ModuleType(name)
+        mod.__spec__ = importlib.machinery.ModuleSpec(name, None)
+        mod.__dict__.update(attrs)
+        monkeypatch.setitem(sys.modules, name, mod)
+        return mod
+    sentinel_lm = lambda *a, **k: "whisper-cpu-logmel"
+    wa = stub("whisper.audio", N_FRAMES=3000, pad_or_trim=lambda *a, **k: "whisper-pad", log_mel_spectrogram=sentinel_lm)
+    wt = stub("whisper.tokenizer", Tokenizer=object, get_tokenizer=lambda *a, **k: None)
+    stub("whisper", audio=wa, tokenizer=wt, load_model=lambda *a, **k: None, log_mel_spectrogram=sentinel_lm,
+         pad_or_trim=wa.pad_or_trim, Whisper=object, DecodingOptions=object)
+    stub("librosa", load=lambda *a, **k: (np.zeros(1, np.float32), 16000))
+    from lyricalignment_b200 import alignment as la_align, audio as la_audio, run_reference
+    run_reference.install("/root/reference")
+    for script in ("inference_alignment", "inference_alignment_nogt"):
+        mod = importlib.import_module(script)
+        assert mod.perform_viterbi_ctc is la_align.perform_viterbi_ctc, script
+        assert mod.perform_viterbi is la_align.perform_viterbi, script
+        if hasattr(mod, "get_mae"):
+            assert mod.get_mae is la_align.get_mae, script
+    am = importlib.import_module("module.align_model")
+    assert am.log_mel_spectrogram is la_audio.log_mel_spectrogram          # module/align_model.py:9,84
+    assert am.pad_or_trim is la_audio.pad_or_trim and am.N_FRAMES == 3000
