@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-head", action="store_true", help="skip the fused-head (N1) legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -437,6 +438,104 @@ def main():
                    "sample": f"first {n_cpu} clips of the workload ({sum(batch.durations[:n_cpu]):.0f} audio-s), same logits "
                              f"(host copies), median of 5 passes, {secs:.2f} s per pass, host cpu_count={os.cpu_count()}"}
 
+    # ---- N1: the head's Linear fused in -- hidden states [sum T][768] instead of logits [sum T][21129] -------------
+    head_leg = None
+    if not args.skip_head:
+        from lyricalignment_b200.head import FusedHead
+        note("fused head (N1)")
+        D = 768
+        torch.manual_seed(114514 + rank)
+        fc = torch.nn.Linear(D, V).to(dev)                                    # random-init head (module/align_model.py:32-33)
+        hidden = torch.nn.functional.mish(torch.randn(total_T, D, device=dev))  # what the Linear sees (:38)
+        fh = FusedHead(fc.weight, fc.bias, device=dev)
+        hev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+
+        def head_step(x, timing=None):
+            job = fh.align_clips_async(x, batch.t_len, batch.labels, timing=timing)
+            r = job.result()
+            job.close()
+            return r
+        head_step(hidden)                                                      # warm-up
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        a.record()
+        for _ in range(reps):
+            r = head_step(hidden, hev)
+        b.record()
+        torch.cuda.synchronize()
+        assert int(r.status.max()) == 0
+        ms_dev = a.elapsed_time(b) / reps
+        ms_emit = hev[0].elapsed_time(hev[1])
+        flops = 2.0 * total_T * V * D
+        tpeak = None
+        try:
+            tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        except Exception:
+            pass
+        # host hidden states: 3 KB per frame over PCIe; 200-clip sub-batches, two jobs in flight (copy || GEMM)
+        hidden_host = hidden.cpu().pin_memory()
+        sub = 200
+        t_off = np.concatenate([[0], np.cumsum(batch.t_len)])
+
+        def head_host_step():
+            jobs, tot = [], 0
+            for b0 in range(0, args.clips, sub):
+                b1 = min(args.clips, b0 + sub)
+                jobs.append(fh.align_clips_async(hidden_host[int(t_off[b0]):int(t_off[b1])], batch.t_len[b0:b1], batch.labels[b0:b1]))
+                if len(jobs) >= 2:
+                    j = jobs.pop(0); tot += len(j.result().first); j.close()
+            for j in jobs:
+                tot += len(j.result().first); j.close()
+            return tot
+
+        # per clip, reference-shaped but with the hidden state instead of the logits (what a caller that adopts
+        # FusedHead writes instead of `fc(...)` + `.cpu()` + perform_viterbi_ctc)
+        wave_host2 = wave.cpu().pin_memory() if args.skip_e2e else wave_host
+        def head_dropin_step():
+            tot = 0
+            for i in range(args.clips):
+                LA.log_mel_spectrogram(wave_host2[w_off[i]:w_off[i] + int(n_samp[i])])
+                out = fh.perform_viterbi_ctc(hidden_host[int(t_off[i]):int(t_off[i + 1])].unsqueeze(0), [batch.labels[i]])
+                tot += len(out[0])
+            return tot
+        head_host_step(); head_dropin_step()
+
+        def timed_wall(fn):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt.item())
+        dt_host = timed_wall(head_host_step)
+        dt_drop = timed_wall(head_dropin_step)
+        tot_audio = float(audio_s.item())
+        head_leg = {
+            "what": "N1: Linear(768 -> 21129) + log-softmax + gather fused (logits never materialised) + K3; inputs are the "
+                    "Mish output [sum T][768] (random-init head, synthetic hidden states)",
+            "device_resident": {"value": round(tot_audio / (ms_dev / 1e3), 1), "unit": "audio-s/s", "ms_per_step": round(ms_dev, 3),
+                                "head_emit_ms": round(ms_emit, 3)},
+            "roofline": {"kernel": "la::head_lse_kernel (split-fp16 tcgen05 GEMM + online LSE) incl. pack + gather", "bound": "tensor",
+                         "achieved": round(3 * flops / (ms_emit / 1e3) / 1e12, 1), "peak": tpeak, "unit": "TFLOP/s",
+                         "frac": round(3 * flops / (ms_emit / 1e3) / 1e12 / tpeak, 4) if tpeak else None,
+                         "useful_tflops": round(flops / (ms_emit / 1e3) / 1e12, 1),
+                         "note": "achieved = issued fp16 MMA FLOPs (3 per useful one: hi*hi + hi*lo + lo*hi) / time of "
+                                 "pack + GEMM + gather; peak = MEASURED_PEAKS.json bf16_tflops_sustained"},
+            "e2e_host_hidden_batched": {"value": round(tot_audio / dt_host, 1), "unit": "audio-s/s",
+                                        "h2d_bytes_per_step": 4.0 * total_T * D * world,
+                                        "call": f"per {sub}-clip sub-batch, two in flight: FusedHead.align_clips_async(pinned host hidden "
+                                                "[sumT,768], t_len, labels).result()"},
+            "e2e_host_hidden_per_clip": {"value": round(tot_audio / dt_drop, 1), "unit": "audio-s/s",
+                                         "h2d_bytes_per_step": (4.0 * total_T * D + 4.0 * float(n_samp.astype(np.int64).sum())) * world,
+                                         "call": "per clip: log_mel_spectrogram(pinned waveform) + FusedHead.perform_viterbi_ctc(pinned "
+                                                 "host hidden[1,T,768], labels) -> nested Python lists"}}
+        del hidden, hidden_host, fh
+
     note("done")
     faulthandler.cancel_dump_traceback_later()
     if rank == 0:
@@ -452,7 +551,7 @@ def main():
                                        "log_mel_spectrogram_ragged + align_clips_async().result())",
                        "l2_policy": f"inputs larger than L2 ({4.0 * total_T * V / 1e9:.1f} GB of logits resident in HBM per GPU)",
                        "parallelism": f"utterance-sharded x{world}" + (", NCCL gather of alignments in the step" if world > 1 else "")},
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "fused_head": head_leg,
             "gpu_launches": launches[0] * args.steps, "clocks": clk,
         }
         print(json.dumps(line))

@@ -419,9 +419,21 @@ int la_head_pack_weights(const float* d_W, int64_t ldw, int V, int D, void* d_pa
     return LA_OK;
 }
 
+// fewer row tiles than SMs (per-clip calls): split the column sweep so the whole chip works on it
+static int head_splits(const la_plan* P, int* per_split) {
+    const int m_tiles = (int)((P->total_T + la::head_tile_rows() - 1) / la::head_tile_rows());
+    const int n_tiles = (P->V + la::head_tile_cols() - 1) / la::head_tile_cols();
+    int want = 1;
+    if (m_tiles > 0 && m_tiles < P->sm_count) want = std::min(n_tiles, (2 * P->sm_count + m_tiles - 1) / m_tiles);
+    const int per = (n_tiles + want - 1) / want;
+    if (per_split) *per_split = per;
+    return (n_tiles + per - 1) / per;
+}
+
 size_t la_head_workspace_bytes(const la_plan* P, int D) {
     if (!P || !head_dim_ok(D)) return 0;
-    return align_up(la::head_packed_bytes(P->total_T, D, false), 256) + align_up((size_t)std::max<int64_t>(P->total_T, 1) * 8, 256);
+    return align_up(la::head_packed_bytes(P->total_T, D, false), 256) +
+           align_up((size_t)std::max<int64_t>(P->total_T, 1) * 8 * head_splits(P, nullptr), 256);
 }
 
 int la_head_emit(const la_plan* P, const float* d_X, int64_t ldx, int D, const float* d_W, int64_t ldw,
@@ -450,11 +462,13 @@ int la_head_emit(const la_plan* P, const float* d_X, int64_t ldx, int D, const f
     hp.V = P->V;
     hp.col_lo = P->mode == LA_MODE_CTC ? 1 : 0;            // utils/alignment.py:123: softmax over [:, :, 1:-1]
     hp.col_hi = P->mode == LA_MODE_CTC ? P->V - 2 : P->V - 1;
+    hp.n_splits = head_splits(P, &hp.n_per_split);
     LA_CUDA(la::launch_head_lse(hp, P->sm_count, st));
     la::HeadGatherParams gp;
     gp.m = P->meta;
     gp.X = d_X; gp.ldx = ldx; gp.W = d_W; gp.ldw = ldw; gp.bias = d_bias;
     gp.lse = hp.lse;
+    gp.n_splits = hp.n_splits;
     gp.E = static_cast<float*>(d_ws);
     gp.rows = P->total_T;
     gp.D = D;

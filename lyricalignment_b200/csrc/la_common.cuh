@@ -128,6 +128,7 @@ struct HeadParams {
     const float* bias;         // [V]
     float2* lse;               // [rows]: (max, sum exp(z - max)) over the softmax columns [col_lo, col_hi]
     int rows, m_tiles, n_tiles, ksteps, V, col_lo, col_hi;
+    int n_splits, n_per_split; // column sweep split over n_splits CTAs per row tile (small batches); lse is [n_splits][rows]
 };
 struct HeadGatherParams {
     BatchMeta m;
@@ -136,7 +137,8 @@ struct HeadGatherParams {
     const float* W;            // [V][D] the Linear's weight
     int64_t ldw;
     const float* bias;         // [V]
-    const float2* lse;         // from head_lse_kernel
+    const float2* lse;         // from head_lse_kernel: [n_splits][rows]
+    int n_splits;
     float* E;                  // the plan's emission area (same layout K2 writes)
     int64_t rows;
     int D;

@@ -17,7 +17,9 @@
 //                       round-to-nearest in the epilogue. A persistent CTA owns a row tile and sweeps all 83 column
 //                       tiles, so the epilogue keeps a per-row online (max, sum exp) pair in registers -- the
 //                       logits go TMEM -> registers -> two floats per row. All CTAs sweep the column tiles in the
-//                       same order, so the 65 MB of packed weights are served from L2.
+//                       same order, so the 65 MB of packed weights are served from L2. A call with fewer row
+//                       tiles than SMs (one clip = 4 tiles) splits the column sweep over several CTAs per row tile;
+//                       the gather kernel merges the partial (max, sum) pairs.
 //   head_gather_kernel  the <= L + 1 columns a frame actually needs (its utterance's labels + the silence / class-0
 //                       column), as exact fp32 dot products on the CUDA cores (63 GFLOP for the whole batch), then
 //                       the reference's emission formulas in its operation order -- the same epilogue as K2.
@@ -168,8 +170,10 @@ __global__ void __launch_bounds__(kHThreads, 1) head_lse_kernel(const HeadParams
         // =============================== producer ==========================================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
-                for (int nt = 0; nt < p.n_tiles; ++nt)
+            for (int w = blockIdx.x; w < p.m_tiles * p.n_splits; w += gridDim.x) {
+                const int mt = w / p.n_splits, sp = w % p.n_splits;
+                const int nt1 = min(p.n_tiles, (sp + 1) * p.n_per_split);
+                for (int nt = sp * p.n_per_split; nt < nt1; ++nt)
                     for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
                         const int s = it % kHStages;
                         mbar_wait(&empty[s], ((it / kHStages) & 1) ^ 1);
@@ -178,14 +182,17 @@ __global__ void __launch_bounds__(kHThreads, 1) head_lse_kernel(const HeadParams
                         bulk_g2s(dst, p.xp + ((size_t)mt * p.ksteps + ks) * (2 * kHABlk), 2 * kHABlk, &full[s]);
                         bulk_g2s(dst + 2 * kHABlk, p.wp + ((size_t)nt * p.ksteps + ks) * (2 * kHBBlk), 2 * kHBBlk, &full[s]);
                     }
+            }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer (whole warp, one elected lane issues) ====
         const uint32_t acc_main = tmem_base, acc_cross = tmem_base + kHN;
         const uint32_t s0 = smem_u32(stages);
         uint32_t it = 0, tc = 0;
-        for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
-            for (int nt = 0; nt < p.n_tiles; ++nt, ++tc) {
+        for (int w = blockIdx.x; w < p.m_tiles * p.n_splits; w += gridDim.x) {
+            const int sp = w % p.n_splits;
+            const int nt1 = min(p.n_tiles, (sp + 1) * p.n_per_split);
+            for (int nt = sp * p.n_per_split; nt < nt1; ++nt, ++tc) {
                 mbar_wait(tmem_empty, (tc & 1) ^ 1);               // the epilogue has read the previous tile out of TMEM
                 h_fence_after();
                 for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
@@ -204,6 +211,7 @@ __global__ void __launch_bounds__(kHThreads, 1) head_lse_kernel(const HeadParams
                 }
                 h_commit(tmem_full);
             }
+        }
     } else if (warp >= 4) {
         // =============================== epilogue: online (max, sum exp) per row ==============
         // thread = row = TMEM lane; warps 4..7 take columns [0,128) of the tile, warps 8..11 [128,256)
@@ -212,9 +220,11 @@ __global__ void __launch_bounds__(kHThreads, 1) head_lse_kernel(const HeadParams
         const int e = tid - 128;                                    // 0..255: which bias column this thread stages
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
         uint32_t tc = 0;
-        for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        for (int w = blockIdx.x; w < p.m_tiles * p.n_splits; w += gridDim.x) {
+            const int mt = w / p.n_splits, sp = w % p.n_splits;
+            const int nt1 = min(p.n_tiles, (sp + 1) * p.n_per_split);
             float m = -INFINITY, s = 0.f;
-            for (int nt = 0; nt < p.n_tiles; ++nt, ++tc) {
+            for (int nt = sp * p.n_per_split; nt < nt1; ++nt, ++tc) {
                 {
                     const int col = nt * kHN + e;
                     bias_s[(tc & 1) * kHN + e] = (col >= p.col_lo && col <= p.col_hi) ? __ldg(p.bias + col) : -INFINITY;
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(kHThreads, 1) head_lse_kernel(const HeadParams
                 const float M = fmaxf(m, o.x);
                 const float S = (m > -INFINITY ? s * expf(m - M) : 0.f) + (o.x > -INFINITY ? o.y * expf(o.x - M) : 0.f);
                 const int64_t grow = (int64_t)mt * kHM + row;
-                if (grow < p.rows) p.lse[grow] = make_float2(M, S);
+                if (grow < p.rows) p.lse[(int64_t)sp * p.rows + grow] = make_float2(M, S);
             }
             named_bar_sync(1, 256);                                 // comb is free for the next row tile
         }
@@ -312,8 +322,13 @@ __global__ void __launch_bounds__(256) head_gather_kernel(const HeadGatherParams
             for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             return acc + __ldg(g.bias + col);
         };
-        const float2 ms = g.lse[row];
-        const float M = ms.x, logS = logf(ms.y);
+        float M = -INFINITY, S = 0.f;                                // the column splits of the row's normaliser meet here
+        for (int sp = 0; sp < g.n_splits; ++sp) M = fmaxf(M, g.lse[(int64_t)sp * g.rows + row].x);
+        for (int sp = 0; sp < g.n_splits; ++sp) {
+            const float2 ms = g.lse[(int64_t)sp * g.rows + row];
+            if (ms.x > -INFINITY) S += ms.y * expf(ms.x - M);
+        }
+        const float logS = logf(S);
         const float zsil = logit(MODE == 0 ? g.m.V - 1 : 0);
         float add = 0.f, blank;
         if (MODE == 0) {
@@ -376,7 +391,7 @@ cudaError_t launch_head_lse(const HeadParams& p, int sm_count, cudaStream_t stre
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
-    head_lse_kernel<<<std::min(p.m_tiles, sm_count), kHThreads, smem, stream>>>(p);
+    head_lse_kernel<<<std::min(p.m_tiles * p.n_splits, sm_count), kHThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

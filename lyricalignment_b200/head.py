@@ -40,6 +40,8 @@ class FusedHead:
         if nbytes == 0:
             raise ValueError("hidden width must be a multiple of 32 in [32, 1024]")
         self.packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._free_ws: list = []                      # recycled (head workspace, plan workspace) pairs: GBs per batch
+        self._copy_stream = torch.cuda.Stream(device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.la_head_pack_weights(self.weight.data_ptr(), self.weight.stride(0), self.V, self.D,
                                                 self.packed.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
@@ -56,7 +58,18 @@ class FusedHead:
             raise ValueError("t_len / labels do not match the hidden states")
         l_len, cols = A._resolve_columns((lens, flat), self.V - 2 if mode == MODE_CTC else self.V - 1)
         with torch.cuda.device(self.device):
-            x = hidden2d.to(self.device, non_blocking=True)
+            if hidden2d.is_cuda:
+                x = hidden2d
+            else:
+                # host hidden states (pin them): the upload runs on a copy stream, so with two jobs in flight the
+                # copy of batch i+1 overlaps the GEMM of batch i; 3 KB per frame instead of 84.5 KB of logits
+                cur = torch.cuda.current_stream(self.device)
+                with torch.cuda.stream(self._copy_stream):
+                    x = hidden2d.to(self.device, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(self._copy_stream)
+                cur.wait_event(done)
+                x.record_stream(cur)
             if x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16:
                 x = x.contiguous().clone()
             plan = A.AlignPlan(mode, self.V, t_len, l_len, cols, self.device.index)
@@ -100,8 +113,15 @@ class HeadJob:
         lib = _lib.load()
         dev = x.device
         self.plan, self._x, self._head = plan, x, head
-        self.ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
-        self.head_ws = torch.empty(int(lib.la_head_workspace_bytes(plan.handle, head.D)), dtype=torch.uint8, device=dev)
+        need_ws, need_hws = plan.workspace_bytes, int(lib.la_head_workspace_bytes(plan.handle, head.D))
+        self.ws = self.head_ws = None
+        for i, (hws, ws) in enumerate(head._free_ws):               # stream-ordered reuse: same stream, so no hazard
+            if hws.numel() >= need_hws and ws.numel() >= need_ws:
+                self.head_ws, self.ws = head._free_ws.pop(i)
+                break
+        if self.ws is None:
+            self.ws = torch.empty(need_ws, dtype=torch.uint8, device=dev)
+            self.head_ws = torch.empty(need_hws, dtype=torch.uint8, device=dev)
         B, Ltot = max(plan.n_utt, 1), max(plan.total_labels, 1)
         self._B, self._Ltot = B, Ltot
         nbytes = 8 * B + 4 * (2 * Ltot + B)
@@ -140,5 +160,7 @@ class HeadJob:
         return self._res
 
     def close(self):
+        if self.ws is not None and len(self._head._free_ws) < 4:
+            self._head._free_ws.append((self.head_ws, self.ws))
         self.ws = self.head_ws = None
         self.plan.close()

@@ -1,15 +1,17 @@
 #!/bin/bash
-# Run on the GPU box (gpurun): launch list of one bench step + full ncu captures of K1/K2/K3.
+# Run on the GPU box (gpurun): launch list of one bench step + full ncu captures of K1/K2/K3/N1.
 # Outputs land in gpurun_out/; scripts/summarize_profiles.py turns them into profiles/*.
 set -x
 mkdir -p gpurun_out
 # only the product's kernels (the synthetic-input generation launches hundreds of torch kernels first)
-ncu --metrics gpu__time_duration.sum --clock-control none \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none \
     -k regex:"emit_kernel|viterbi_kernel|logmel_kernel|logmel_floor_kernel|logmel_init_kernel|gather_logp_kernel" \
     -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --skip-e2e > gpurun_out/launches_bench.log 2>&1
+    python bench.py --steps 2 --warmup 3 --skip-e2e --skip-head > gpurun_out/launches_bench.log 2>&1
 for k in emit_kernel logmel_kernel viterbi_kernel; do
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 2 -o gpurun_out/$k -f \
-      python bench.py --clips 400 --steps 2 --warmup 3 --skip-e2e > gpurun_out/ncu_$k.log 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 2 -o gpurun_out/$k -f \
+      python bench.py --clips 400 --steps 2 --warmup 3 --skip-e2e --skip-head > gpurun_out/ncu_$k.log 2>&1
 done
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:head_lse_kernel -s 1 -c 1 -o gpurun_out/head_lse_kernel -f \
+    python scripts/bench_head.py 400 > gpurun_out/ncu_head_lse_kernel.log 2>&1
 ls -la gpurun_out

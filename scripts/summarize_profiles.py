@@ -51,7 +51,7 @@ def launches():
     total = sum(sum(v) for v in agg.values())
     ours = total
     with open(os.path.join(OUT, f"launches_{TAG}.md"), "w") as f:
-        f.write(f"# ncu launch list ({TAG}): `python bench.py --steps 2 --warmup 3 --skip-e2e` under "
+        f.write(f"# ncu launch list ({TAG}): `python bench.py --steps 2 --warmup 3 --skip-e2e --skip-head` under "
                 "`ncu --metrics gpu__time_duration.sum --clock-control none`\n\n"
                 "Per-launch times are cold-cache and serialised: compare SHARES, not absolutes. Filtered to the\n"
                 "product's kernels (`-k regex:emit_kernel|viterbi_kernel|logmel...`): 5 steps (3 warm-up + 2 timed) of the\n"
@@ -78,7 +78,8 @@ def full(name, pretty):
     out = {}
     with open(os.path.join(OUT, f"{pretty}_{TAG}.md"), "w") as f:
         f.write(f"# ncu --set full: {pretty} ({TAG})\n\nCommand: `ncu --set full --clock-control none --import-source on -k regex:{name} -s 3 -c 2 "
-                "python bench.py --clips 400 --steps 2 --warmup 3 --skip-e2e` (400 clips keep the 40 replay passes short).\n\n")
+                "python bench.py --clips 400 --steps 2 --warmup 3 --skip-e2e --skip-head` (400 clips keep the 40 replay passes short; "
+                "N1: `python scripts/bench_head.py 400`).\n\n")
         for li, vals in enumerate(rows[2:]):
             d = dict(zip(hdr, vals))
             f.write(f"## launch {li}: `{d.get('Kernel Name','')[:100]}` grid {d.get('launch__grid_size','?')} block {d.get('launch__block_size','?')}\n\n| metric | value | unit |\n|---|---|---|\n")
@@ -103,6 +104,7 @@ if __name__ == "__main__":
     k2 = full("emit_kernel", "k2_emit")
     full("logmel_kernel", "k1_logmel")
     full("viterbi_kernel", "k3_viterbi")
+    full("head_lse_kernel", "n1_head_lse")
     if k2:
         rd = to_bytes(k2["dram__bytes_read.sum"], k2["_units"]["dram__bytes_read.sum"])
         wr = to_bytes(k2["dram__bytes_write.sum"], k2["_units"]["dram__bytes_write.sum"])

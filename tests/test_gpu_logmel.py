@@ -1,11 +1,11 @@
 """GPU: K1 (tcgen05 log-mel) against the fp64 oracle restatement.
 
-Tolerance. BASELINE.json:north_star asks for 1e-4 absolute in the log10 domain (== 2.5e-5 after
-the final /4). Measured on B200 (scripts/diag_logmel.py, profiles/logmel_precision_r1.txt): the
-kernel's operands carry fp32-level precision (3xTF32), so like ANY fp32 DFT its error is set by
-weak single-bin mel filters (mel 13/14 are one FFT bin wide): 99.9 % of the cells are within
-6e-6, the worst cell seen is 1.0e-4; the reference's own fp32 torch.stft path sits 2e-5..7e-5
-from the same fp64 oracle. The test therefore pins p99.9 <= 2e-5 and max <= 2e-4 (log10 units)."""
+Tolerance. BASELINE.json:north_star asks for 1e-4 absolute in the log10 domain (== 2.5e-5 after the final /4) and
+that is what every case asserts, on EVERY cell, the 5-minute song included -- no percentile allowance. Measured on
+B200 (scripts/diag_logmel*.py, profiles/logmel_precision_r2.txt): worst cell 8.0e-6 on the 5-minute song, 1.0e-5 on
+noise; the reference's own fp32 torch.stft path sits 2.7e-5 .. 8.2e-5 from the same oracle. (Round 1's 3xTF32 chain
+with the tensor core's truncating accumulate was at 3.3e-4; round 2 slices the operands on a fixed grid so that the
+leading chain is exact in fp32 -- see la_logmel.cu.) p99.9 is pinned an order of magnitude below the bar as well."""
 import numpy as np
 import pytest
 import torch
@@ -16,8 +16,8 @@ pytestmark = pytest.mark.gpu
 
 from lyricalignment_b200 import audio as LA    # noqa: E402
 
-TOL = 2e-4 / 4.0          # worst cell, output units
-TOL_P999 = 2e-5 / 4.0     # 99.9th percentile
+TOL = 1e-4 / 4.0          # worst cell, output units == 1e-4 in the log10 domain
+TOL_P999 = 1e-5 / 4.0     # 99.9th percentile
 
 
 def _close(got, want):
@@ -103,10 +103,9 @@ def test_five_minute_song_and_chunked_framing():
     a = _signal(rng, 16000 * 300, "survey")
     got = LA.log_mel_spectrogram(a).cpu().numpy()
     assert got.shape == (80, 30000)
-    # 2.4 M cells: the tail of the error distribution shows (measured: 7 cells above 1e-4, worst 3.3e-4
-    # in the log10 domain, all at the one-bin-wide filters; p99.99 1.7e-5) -- see DESIGN.md section 2
+    # 2.4 M cells, every one of them within the north_star bound (measured worst: 8.0e-6)
     e = 4.0 * np.abs(got - oracle.log_mel_spectrogram(a))
-    assert e.max() <= 6e-4 and np.quantile(e, 0.9999) <= 4e-5 and (e > 1e-4).mean() <= 2e-5
+    assert e.max() <= 1e-4 and np.quantile(e, 0.9999) <= 1e-5, (float(e.max()), float(np.quantile(e, 0.9999)))
     assert sum(LA.decode_frames(min(3000, 30000 - s)) for s in range(0, 30000, 3000)) == 15000
 
 
