@@ -31,14 +31,14 @@ int set_error(int code, const char* msg) { return fail(code, msg); }
 void logmel_release_tables();
 }
 
-// K3 launch shapes: one pair (blank + label state) per lane wherever possible -- the frame step is a
-// dependent chain whose length grows with the pairs a lane owns, so lanes are spent before pairs
-// per lane. One CTA per utterance using exactly ceil(pairs / 32K) warps (the launch is sized for the
-// widest utterance of its bucket, surplus warps exit). Buckets 0..2: K = 1 with up to 2 / 8 / 32
-// warps (so a batch of ordinary clips is ONE launch); 3..5: 32 warps with 2 / 4 / 8 pairs per lane.
-constexpr int kBuckets = 6;
+// K3 launch shapes {pairs per lane, max warps}. One CTA per utterance using exactly ceil(pairs / 32K) warps (the
+// launch is sized for the widest utterance of its bucket, surplus warps exit). A lone warp is bound by its own
+// dependent instruction stream, so up to 32 pairs it gets one pair per lane, and from 33 pairs on TWO: the two
+// chains of a lane overlap their latencies and the warp count (= the issue load of a batch, and the number of
+// hand-offs of a long utterance) halves. Four / eight pairs per lane only where 32 warps would not suffice.
+constexpr int kBuckets = 7;
 struct BucketShape { int K; int max_warps; };
-static const BucketShape kShape[kBuckets] = {{1, 2}, {1, 8}, {1, 32}, {2, 32}, {4, 32}, {8, 32}};
+static const BucketShape kShape[kBuckets] = {{1, 1}, {2, 1}, {2, 4}, {2, 16}, {2, 32}, {4, 32}, {8, 32}};
 static int bucket_for_pairs(int pairs) {
     for (int b = 0; b < kBuckets; ++b)
         if (pairs <= 32 * kShape[b].K * kShape[b].max_warps) return b;

@@ -23,6 +23,9 @@
 // Emission rows ([T][row_floats], col 0 = blank) are streamed in chunks of up to 32 frames into a
 // 3- or 4-deep shared-memory ring by 1-D TMA bulk copies issued by the last warp. Backpointers are
 // 2-bit step codes (k - bt), one nibble per pair per frame, 8 frames per 32-bit word, written coalesced.
+// Launch shapes (la_api.cu): one pair per lane up to 32 pairs, then TWO pairs per lane (a 41-pair clip is one
+// warp, not two: two independent chains per lane overlap their latencies, and half the warps means half the
+// instruction issue for a batch of clips), four / eight beyond 2048 / 4096 pairs.
 // The backtrace is a single warp walking t = T-1..1: lanes hold a 32-pair window of the current
 // 8-frame block in registers (next block prefetched); the walker takes the current pair's word by
 // shuffle and jumps straight to the next frame whose code is non-zero (count-leading-zeros on the
@@ -67,8 +70,8 @@ __device__ __forceinline__ void ring_put(uint32_t addr, double v, uint32_t pred)
 
 // K = pairs per thread, DUMP = parity instrumentation (full fp64 table to global memory; compiled out of
 // the production kernels)
-template <int K, bool DUMP>
-__global__ void __launch_bounds__(1024) viterbi_kernel(const VitParams p) {
+template <int K, bool DUMP, int MAXT>
+__global__ void __launch_bounds__(MAXT) viterbi_kernel(const VitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw_launch = blockDim.x >> 5;
@@ -204,42 +207,54 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(const VitParams p) {
             for (int j = 0; j < K; ++j) acc[j] = 0u;
         }
     };
-    // eight frames t .. t+7 (t a multiple of 8, t >= 8, all inside one chunk), one pair per lane: the
-    // emissions of the whole block are promoted to fp64 up front, shifts and ring offsets are immediates,
-    // and the only per-frame work left is the dependent chain itself
+    // eight frames t .. t+7 (t a multiple of 8, t >= 8, all inside one chunk), K <= 2 pairs per lane: the
+    // emissions of the whole block are in registers up front, shifts and ring offsets are immediates, and the
+    // only per-frame work left is the dependent chain itself (two independent ones per lane when K = 2, which is
+    // what lets a lone warp overlap their latencies)
     auto block8 = [&](int t, const float* r0, auto HL) {
         constexpr bool kHasLeft = decltype(HL)::value;
-        double ebv[8], elv[8];
+        float ebf[8], elf[8][K];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            ebv[i] = (double)r0[i * wrow];
-            elv[i] = (double)r0[i * wrow + ecol[0]];
+            ebf[i] = r0[i * wrow];
+#pragma unroll
+            for (int j = 0; j < K; ++j) elf[i][j] = r0[i * wrow + ecol[j]];
         }
         const uint32_t put8 = put_base + (((uint32_t)t * 8u) & ring_mask8);            // slots t .. t+7 are contiguous
         const uint32_t take0 = take_base + (((uint32_t)(t - 1) * 8u) & ring_mask8);    // slot t-1
         const uint32_t take8 = take_base + (((uint32_t)t * 8u) & ring_mask8);          // slots t .. t+6 feed frames t+1 .. t+7
-        uint32_t a = 0u;
-        double b = pb[0], l = pl[0];
+        uint32_t a[K];
+        double b[K], l[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) { a[j] = 0u; b[j] = pb[j]; l[j] = pl[j]; }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            double q = shfl_up_f64(l, 1);
+            double q = shfl_up_f64(l[K - 1], 1);
             if (kHasLeft) {
                 const double v = ring_take(i == 0 ? take0 : take8 + 8u * (uint32_t)(i - 1), rearm);
                 q = lane0 ? v : q;
             } else {
                 q = lane0 ? -INFINITY : q;
             }
-            const bool b_stay = b > q;
-            const bool skip = (q >= b) && (q >= l) && skip_ok[0];
-            const bool l_stay = l > b;
-            const double nb = (b_stay ? b : q) + ebv[i];
-            l = (skip ? q : (l_stay ? l : b)) + elv[i];
-            b = nb;
-            ring_put(put8 + 8u * (uint32_t)i, l, put_pred);
-            a |= ((b_stay ? 0u : 1u) | (skip ? 4u : (l_stay ? 0u : 2u))) << (4 * i);
+            const double eb = (double)ebf[i];
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const double bj = b[j], lj = l[j];
+                const bool b_stay = bj > q;
+                const bool skip = (q >= bj) && (q >= lj) && skip_ok[j];
+                const bool l_stay = lj > bj;
+                b[j] = (b_stay ? bj : q) + eb;
+                l[j] = (skip ? q : (l_stay ? lj : bj)) + (double)elf[i][j];
+                a[j] |= ((b_stay ? 0u : 1u) | (skip ? 4u : (l_stay ? 0u : 2u))) << (4 * i);
+                q = lj;                                    // left neighbour of pair j+1 (old value)
+            }
+            ring_put(put8 + 8u * (uint32_t)i, l[K - 1], put_pred);
         }
-        pb[0] = b; pl[0] = l;
-        bp[(int64_t)(t >> 3) * pairs_pad + pair0] = a;
+#pragma unroll
+        for (int j = 0; j < K; ++j) { pb[j] = b[j]; pl[j] = l[j]; }
+        uint32_t* w = bp + (int64_t)(t >> 3) * pairs_pad + pair0;
+        if (K == 2) *reinterpret_cast<uint2*>(w) = make_uint2(a[0], a[1]);
+        else w[0] = a[0];
     };
 
     const long long c_fwd0 = clock64();
@@ -256,7 +271,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(const VitParams p) {
         int tt = 0;
         while (tt < nt) {
             const int t = t0 + tt;
-            if (K == 1 && !DUMP && (t & 7) == 0 && t >= 8 && tt + 8 <= nt) {
+            if (K <= 2 && !DUMP && (t & 7) == 0 && t >= 8 && tt + 8 <= nt) {
                 if (has_left) block8(t, rows + tt * wrow, std::true_type{});
                 else block8(t, rows + tt * wrow, std::false_type{});
                 tt += 8;
@@ -356,9 +371,9 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(const VitParams p) {
 }
 
 // frames per chunk: a power of two (8-frame blocks and the hand-off ring index with masks), at most 32, and
-// small enough that four stages of the widest row fit in shared memory
+// small enough that four stages of the widest row (<= 4 x 48 KB) plus the hand-off ring fit in shared memory
 int viterbi_chunk_frames(int row_floats_max) {
-    const int fit = (36 * 1024) / (row_floats_max * 4);
+    const int fit = (48 * 1024) / (row_floats_max * 4);
     int c = kVitChunkMax;
     while (c > 1 && c > fit) c >>= 1;
     return c;
@@ -375,7 +390,7 @@ size_t viterbi_smem_bytes(int row_floats_max, int chunk, int stages, int ring, i
     return (size_t)stages * chunk * row_floats_max * 4 + 2 * kVitStagesMax * 8 + 16 + (size_t)ring * warps * 8;
 }
 
-template <int K>
+template <int K, int MAXT>
 static cudaError_t launch_one(const VitParams& p, int threads, int grid, size_t smem, cudaStream_t stream) {
     // the opt-in is a per-function attribute of the loaded module: set once per (function, device), not per launch
     static bool attr_done[2][64] = {};
@@ -384,17 +399,18 @@ static cudaError_t launch_one(const VitParams& p, int threads, int grid, size_t 
     const int d = p.dp_dump ? 1 : 0;
     if (dev >= 0 && dev < 64 && !attr_done[d][dev]) {
         cudaError_t e = p.dp_dump
-            ? cudaFuncSetAttribute(viterbi_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
-            : cudaFuncSetAttribute(viterbi_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            ? cudaFuncSetAttribute(viterbi_kernel<K, true, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)
+            : cudaFuncSetAttribute(viterbi_kernel<K, false, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e != cudaSuccess) return e;
         attr_done[d][dev] = true;
     }
-    if (p.dp_dump) viterbi_kernel<K, true><<<grid, threads, smem, stream>>>(p);
-    else viterbi_kernel<K, false><<<grid, threads, smem, stream>>>(p);
+    if (p.dp_dump) viterbi_kernel<K, true, MAXT><<<grid, threads, smem, stream>>>(p);
+    else viterbi_kernel<K, false, MAXT><<<grid, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-// K pairs per lane; one CTA of `warps` warps per utterance
+// K pairs per lane; one CTA of `warps` warps per utterance. CTAs of up to 16 warps are compiled with a 512-thread
+// bound (128 registers: the unrolled 8-frame block keeps 8 x (1 + K) emissions live), the 32-warp shapes with 1024.
 cudaError_t launch_viterbi(const VitParams& p_in, int K, int warps, cudaStream_t stream) {
     if (p_in.n_order <= 0) return cudaSuccess;
     VitParams p = p_in;
@@ -403,11 +419,16 @@ cudaError_t launch_viterbi(const VitParams& p_in, int K, int warps, cudaStream_t
     p.stages = viterbi_stages(warps);
     p.ring = viterbi_ring(p.chunk, p.stages);
     const size_t smem = viterbi_smem_bytes(p.row_floats_max, p.chunk, p.stages, p.ring, warps);
+    const int threads = 32 * warps;
+    if (warps <= 16) {
+        if (K == 1) return launch_one<1, 512>(p, threads, p.n_order, smem, stream);
+        if (K == 2) return launch_one<2, 512>(p, threads, p.n_order, smem, stream);
+    }
     switch (K) {
-        case 1: return launch_one<1>(p, 32 * warps, p.n_order, smem, stream);
-        case 2: return launch_one<2>(p, 32 * warps, p.n_order, smem, stream);
-        case 4: return launch_one<4>(p, 32 * warps, p.n_order, smem, stream);
-        default: return launch_one<8>(p, 32 * warps, p.n_order, smem, stream);
+        case 1: return launch_one<1, 1024>(p, threads, p.n_order, smem, stream);
+        case 2: return launch_one<2, 1024>(p, threads, p.n_order, smem, stream);
+        case 4: return launch_one<4, 1024>(p, threads, p.n_order, smem, stream);
+        default: return launch_one<8, 1024>(p, threads, p.n_order, smem, stream);
     }
 }
 
