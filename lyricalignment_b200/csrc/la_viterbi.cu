@@ -32,6 +32,7 @@
 // masked word), so its cost is one step per block plus one per transition, not one per frame.
 // Lane 0 emits first / last+1 at every label-state run boundary (the path is monotone, so each
 // label's occupancy is one run).
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -114,10 +115,9 @@ __global__ void __launch_bounds__(MAXT) viterbi_kernel(const VitParams p) {
     __syncthreads();
 
     const int nchunks = (T + chunk - 1) / chunk;
-    auto issue = [&](int c) {
+    auto issue = [&](int c, int s) {                      // chunk c into stage s (= c % stages; the callers track it)
         const int rows = min(chunk, T - c * chunk);
         const uint32_t bytes = (uint32_t)rows * wrow * 4;
-        const int s = c % stages;
         fence_proxy_async();
         mbar_arrive_expect_tx(&full[s], bytes);
         bulk_g2s(reinterpret_cast<unsigned char*>(stage0) + s * stage_bytes, E + (int64_t)c * chunk * wrow, bytes, &full[s]);
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(MAXT) viterbi_kernel(const VitParams p) {
     // leading warp -- up to nwarps frames ahead -- still has stages-1 chunks of emissions staged.
     const bool loader = (warp == nwarps - 1) && lane == 0;
     if (loader)
-        for (int c = 0; c < min(stages, nchunks); ++c) issue(c);
+        for (int c = 0; c < min(stages, nchunks); ++c) issue(c, c);
 
     // ---- per-pair constants ------------------------------------------------------------
     const int pair0 = tid * K;
@@ -258,13 +258,13 @@ __global__ void __launch_bounds__(MAXT) viterbi_kernel(const VitParams p) {
     };
 
     const long long c_fwd0 = clock64();
+    int s = 0, ph = 0, sp = 0, php = 0;                    // stage / phase parity of chunk c and of chunk c-1 (no div/mod per chunk)
     for (int c = 0; c < nchunks; ++c) {
-        const int s = c % stages;
         if (loader && c >= 1 && c - 1 + stages < nchunks) {
-            mbar_wait(&empty[(c - 1) % stages], ((c - 1) / stages) & 1);   // every warp has left chunk c-1
-            issue(c - 1 + stages);
+            mbar_wait(&empty[sp], php);                    // every warp has left chunk c-1
+            issue(c - 1 + stages, sp);
         }
-        mbar_wait(&full[s], (c / stages) & 1);
+        mbar_wait(&full[s], ph);
         const float* rows = stage0 + s * (stage_bytes / 4);
         const int t0 = c * chunk;
         const int nt = min(chunk, T - t0);
@@ -286,6 +286,8 @@ __global__ void __launch_bounds__(MAXT) viterbi_kernel(const VitParams p) {
         }
         __syncwarp();
         if (lane0) mbar_arrive(&empty[s]);                 // this warp no longer reads stage s
+        sp = s; php = ph;
+        if (++s == stages) { s = 0; ph ^= 1; }
     }
 
     // ---- end-state pick (utils/alignment.py:157): S-1 iff dp[T-1][S-1] > dp[T-1][S-2] --------
@@ -370,16 +372,26 @@ __global__ void __launch_bounds__(MAXT) viterbi_kernel(const VitParams p) {
     }
 }
 
-// frames per chunk: a power of two (8-frame blocks and the hand-off ring index with masks), at most 32, and
-// small enough that four stages of the widest row (<= 4 x 48 KB) plus the hand-off ring fit in shared memory
+// frames per chunk: a power of two (8-frame blocks and the hand-off ring index with masks), at most 32. The
+// per-chunk bookkeeping (barrier waits, refill) is worth ~700 cycles, so wide rows get the biggest chunk of which
+// TWO stages still fit in 160 KB (the refill distance is then one chunk = 32 frames = ~6 us, far more than the
+// copy needs), narrow rows keep 32-frame chunks with three or four stages.
 int viterbi_chunk_frames(int row_floats_max) {
-    const int fit = (48 * 1024) / (row_floats_max * 4);
+    const int fit = (80 * 1024) / (row_floats_max * 4);
     int c = kVitChunkMax;
     while (c > 1 && c > fit) c >>= 1;
     return c;
 }
-// the leading warp runs up to `warps` frames ahead of the last one: give wide utterances one more stage
-static int viterbi_stages(int warps) { return warps > 4 ? 4 : 3; }
+// the leading warp runs up to `warps` frames ahead of the last one, and a stage is only refilled once every warp
+// has left it: (stages - 1) chunks must cover that skew
+static int viterbi_stages(int warps, int chunk, int row_floats_max) {
+    const int stage_bytes = chunk * row_floats_max * 4;
+    const int fit = std::max(2, std::min(kVitStagesMax, (160 * 1024) / std::max(stage_bytes, 1)));
+    const int want = warps > 4 ? 4 : 3;
+    int st = std::min(want, fit);
+    while (st < kVitStagesMax && (st - 1) * chunk < warps + 8 && (st + 1) * stage_bytes <= 200 * 1024) ++st;
+    return st;
+}
 static int viterbi_ring(int chunk, int stages) {
     int r = 16;
     while (r < stages * chunk) r <<= 1;
@@ -416,7 +428,7 @@ cudaError_t launch_viterbi(const VitParams& p_in, int K, int warps, cudaStream_t
     VitParams p = p_in;
     static const int trace = [] { const char* e = getenv("LA_VIT_TRACE"); return e ? atoi(e) : 0; }();
     p.trace = trace;
-    p.stages = viterbi_stages(warps);
+    p.stages = viterbi_stages(warps, p.chunk, p.row_floats_max);
     p.ring = viterbi_ring(p.chunk, p.stages);
     const size_t smem = viterbi_smem_bytes(p.row_floats_max, p.chunk, p.stages, p.ring, warps);
     const int threads = 32 * warps;
