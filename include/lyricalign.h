@@ -96,10 +96,16 @@ int64_t la_plan_total_labels(const la_plan* plan);
 int la_plan_num_launches(const la_plan* plan);
 /* introspection for tests: where utterance u's emission rows / packed backpointers live in
  * the workspace. emit: float32 [T_u][row_floats], column 0 = blank/silence, column 1+l =
- * label l. bp: uint32 [ceil(T_u/8)][pairs_padded], nibble (t%8) of word [t/8][i] =
+ * label l. bp: uint32 [word_rows][pairs_padded] (see la_plan_utt_bp_layout), one nibble per pair per frame =
  * code(blank state 2i) | code(label state 2i+1) << 1, code = k - backpointer in {0,1,2}. */
 int la_plan_utt_layout(const la_plan* plan, int utt, int64_t* emit_off_bytes, int32_t* row_floats,
                        int64_t* bp_off_bytes, int32_t* pairs_padded);
+/* introspection for tests, second half: how K3 lays utterance u's backpointers out. The packed table is
+ * uint32 [word_rows][pairs_padded]; pair i lives in column i + col_shift. skew_log2k < 0: the row-synchronous
+ * kernel, nibble t%8 of word row t/8 is frame t. skew_log2k >= 0: the wavefront kernel (utterances of up to 63
+ * pairs) -- the lane that owns column c runs s = (c >> skew_log2k) & 31 frames behind lane 0, and nibble n of
+ * word row r of column c is frame 8r + n - s (so word_rows = ceil((T_u + 31) / 8)). */
+int la_plan_utt_bp_layout(const la_plan* plan, int utt, int32_t* word_rows, int32_t* col_shift, int32_t* skew_log2k);
 
 /* ---- K2: fused log-softmax + label gather ----------------------------------------------
  * Replaces utils/alignment.py:123-134 (mode CTC) / :14-20 (mode CE): one streaming pass over

@@ -31,16 +31,18 @@ int set_error(int code, const char* msg) { return fail(code, msg); }
 void logmel_release_tables();
 }
 
-// K3 launch shapes {pairs per lane, max warps}. One CTA per utterance using exactly ceil(pairs / 32K) warps (the
-// launch is sized for the widest utterance of its bucket, surplus warps exit). A lone warp is bound by its own
-// dependent instruction stream, so up to 32 pairs it gets one pair per lane, and from 33 pairs on TWO: the two
-// chains of a lane overlap their latencies and the warp count (= the issue load of a batch, and the number of
-// hand-offs of a long utterance) halves. Four / eight pairs per lane only where 32 warps would not suffice.
-constexpr int kBuckets = 7;
+// K3 launch shapes. Bucket 0: the wavefront kernel (la_viterbi.cu, viterbi_skew_kernel), one warp per utterance,
+// up to 63 pairs (one pair per lane up to 32 pairs, two from 33 on -- the choice is made per utterance inside ONE
+// launch). The other buckets: the row-synchronous pipeline kernel, {pairs per lane, max warps}, one CTA per
+// utterance using exactly ceil(pairs / 32K) warps (the launch is sized for the widest utterance of its bucket,
+// surplus warps exit).
+constexpr int kBuckets = 6;
 struct BucketShape { int K; int max_warps; };
-static const BucketShape kShape[kBuckets] = {{1, 1}, {2, 1}, {2, 4}, {2, 16}, {2, 32}, {4, 32}, {8, 32}};
+static const BucketShape kShape[kBuckets] = {{0, 1}, {2, 4}, {2, 16}, {2, 32}, {4, 32}, {8, 32}};
+constexpr int kSkewMaxPairs = 63;
 static int bucket_for_pairs(int pairs) {
-    for (int b = 0; b < kBuckets; ++b)
+    if (pairs <= kSkewMaxPairs) return 0;
+    for (int b = 1; b < kBuckets; ++b)
         if (pairs <= 32 * kShape[b].K * kShape[b].max_warps) return b;
     return kBuckets - 1;
 }
@@ -261,16 +263,27 @@ static int plan_create_impl(la_plan** out, int mode, int n_utt, int V, const int
         P->row_max[b] = std::max(P->row_max[b], P->e_row[u]);
         P->order[b].push_back(u);
     }
+    // longest utterance first: one CTA per utterance, dispatched in grid order, so the tail of a launch is its
+    // shortest clips rather than whichever long one happened to come last
+    for (int b = 0; b < kBuckets; ++b)
+        std::stable_sort(P->order[b].begin(), P->order[b].end(),
+                         [&](int32_t x, int32_t y) { return h_t_len[x] > h_t_len[y]; });
     size_t e_floats = 0, bp_words = 0;
     for (int u = 0; u < n_utt; ++u) {
         const BucketShape& sh = kShape[bucket_of[u]];
-        const int warps = std::max(1, (h_l_len[u] + 1 + 32 * sh.K - 1) / (32 * sh.K));
-        P->warps_max[bucket_of[u]] = std::max(P->warps_max[bucket_of[u]], warps);
-        P->bp_pairs[u] = 32 * warps * sh.K;
         P->e_off[u] = (int64_t)e_floats;
         e_floats += (size_t)h_t_len[u] * P->e_row[u];
         P->bp_off[u] = (int64_t)bp_words;
-        bp_words += (size_t)((h_t_len[u] + 7) / 8) * P->bp_pairs[u];
+        if (bucket_of[u] == 0) {                                   // wavefront kernel: word rows count STEPS (frames + up to 31)
+            P->warps_max[0] = 1;
+            P->bp_pairs[u] = (h_l_len[u] + 1 <= 32) ? 32 : 64;
+            bp_words += (size_t)((h_t_len[u] + 31 + 7) / 8) * P->bp_pairs[u];
+        } else {
+            const int warps = std::max(1, (h_l_len[u] + 1 + 32 * sh.K - 1) / (32 * sh.K));
+            P->warps_max[bucket_of[u]] = std::max(P->warps_max[bucket_of[u]], warps);
+            P->bp_pairs[u] = 32 * warps * sh.K;
+            bp_words += (size_t)((h_t_len[u] + 7) / 8) * P->bp_pairs[u];
+        }
     }
     P->emit_bytes = align_up(e_floats * 4 + 16, 256);
     P->bp_bytes = align_up(bp_words * 4 + 16, 256);
@@ -344,6 +357,18 @@ int la_plan_utt_layout(const la_plan* P, int utt, int64_t* emit_off_bytes, int32
     return LA_OK;
 }
 
+int la_plan_utt_bp_layout(const la_plan* P, int utt, int32_t* word_rows, int32_t* col_shift, int32_t* skew_log2k) {
+    if (!P || utt < 0 || utt >= P->n_utt) return fail(LA_ERR_ARG, "bad utterance index");
+    const int T = P->t_off[utt + 1] - P->t_off[utt];
+    const int L = P->l_off[utt + 1] - P->l_off[utt];
+    const bool skew = bucket_for_pairs(L + 1) == 0;
+    const int k2 = skew && L + 1 > 32;
+    if (word_rows) *word_rows = skew ? (T + 31 + 7) / 8 : (T + 7) / 8;
+    if (col_shift) *col_shift = k2 ? 1 : 0;
+    if (skew_log2k) *skew_log2k = skew ? k2 : -1;
+    return LA_OK;
+}
+
 // rows [row0, row0 + n_rows) of the batch; d_logits points at row `row0`
 static int emit_rows(const la_plan* P, const float* d_logits, int64_t ld, const float* d_sil,
                      int64_t ld_sil, void* d_ws, int64_t row0, int64_t n_rows, cudaStream_t stream);
@@ -377,7 +402,8 @@ static int viterbi_impl(const la_plan* P, void* d_ws, int32_t* d_first, int32_t*
         vp.chunk = la::viterbi_chunk_frames(P->row_max[b]);
         vp.first = d_first; vp.last_plus1 = d_last; vp.score = d_score; vp.status = d_status;
         vp.dp_dump = d_dp;
-        LA_CUDA(la::launch_viterbi(vp, kShape[b].K, P->warps_max[b], static_cast<cudaStream_t>(stream)));
+        if (b == 0) LA_CUDA(la::launch_viterbi_skew(vp, static_cast<cudaStream_t>(stream)));
+        else LA_CUDA(la::launch_viterbi(vp, kShape[b].K, P->warps_max[b], static_cast<cudaStream_t>(stream)));
     }
     P->last_stream = static_cast<cudaStream_t>(stream);
     P->used = true;
