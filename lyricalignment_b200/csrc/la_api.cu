@@ -31,19 +31,18 @@ int set_error(int code, const char* msg) { return fail(code, msg); }
 void logmel_release_tables();
 }
 
-// K3 launch shapes. Bucket 0: the wavefront kernel (la_viterbi.cu, viterbi_skew_kernel), one warp per utterance,
-// up to 63 pairs (one pair per lane up to 32 pairs, two from 33 on -- the choice is made per utterance inside ONE
-// launch). The other buckets: the row-synchronous pipeline kernel, {pairs per lane, max warps}, one CTA per
-// utterance using exactly ceil(pairs / 32K) warps (the launch is sized for the widest utterance of its bucket,
-// surplus warps exit).
-constexpr int kBuckets = 6;
+// K3 launch shapes. Buckets 0-2: the wavefront kernel (la_viterbi_wave.cuh): one warp per utterance up to 63 pairs
+// (one pair per lane up to 32 pairs, two from 33 on -- chosen per utterance inside ONE launch), then 64 columns per
+// warp on up to 4 / up to 10 warps. The other buckets: the row-synchronous pipeline kernel, {pairs per lane, max
+// warps}. One CTA per utterance; a launch is sized for the widest utterance of its bucket, surplus warps exit.
+constexpr int kBuckets = 7;
+constexpr int kWaveBuckets = 3;
 struct BucketShape { int K; int max_warps; };
-static const BucketShape kShape[kBuckets] = {{0, 1}, {2, 4}, {2, 16}, {2, 32}, {4, 32}, {8, 32}};
-constexpr int kSkewMaxPairs = 63;
+static const BucketShape kShape[kBuckets] = {{0, 1}, {2, 4}, {2, 10}, {2, 16}, {2, 32}, {4, 32}, {8, 32}};
 static int bucket_for_pairs(int pairs) {
-    if (pairs <= kSkewMaxPairs) return 0;
-    for (int b = 1; b < kBuckets; ++b)
-        if (pairs <= 32 * kShape[b].K * kShape[b].max_warps) return b;
+    if (pairs <= 63) return 0;
+    for (int b = 1; b < kBuckets; ++b)                        // wave shapes: pair i lives in column i + 1
+        if (pairs + (b < kWaveBuckets ? 1 : 0) <= 32 * kShape[b].K * kShape[b].max_warps) return b;
     return kBuckets - 1;
 }
 
@@ -274,9 +273,11 @@ static int plan_create_impl(la_plan** out, int mode, int n_utt, int V, const int
         P->e_off[u] = (int64_t)e_floats;
         e_floats += (size_t)h_t_len[u] * P->e_row[u];
         P->bp_off[u] = (int64_t)bp_words;
-        if (bucket_of[u] == 0) {                                   // wavefront kernel: word rows count STEPS (frames + up to 31)
-            P->warps_max[0] = 1;
-            P->bp_pairs[u] = (h_l_len[u] + 1 <= 32) ? 32 : 64;
+        if (bucket_of[u] < kWaveBuckets) {                         // wavefront kernel: word rows count STEPS (frames + up to 31)
+            const int pairs = h_l_len[u] + 1;
+            const int warps = bucket_of[u] == 0 ? 1 : (pairs + 1 + 63) / 64;
+            P->warps_max[bucket_of[u]] = std::max(P->warps_max[bucket_of[u]], warps);
+            P->bp_pairs[u] = bucket_of[u] == 0 ? (pairs <= 32 ? 32 : 64) : 64 * warps;
             bp_words += (size_t)((h_t_len[u] + 31 + 7) / 8) * P->bp_pairs[u];
         } else {
             const int warps = std::max(1, (h_l_len[u] + 1 + 32 * sh.K - 1) / (32 * sh.K));
@@ -361,7 +362,7 @@ int la_plan_utt_bp_layout(const la_plan* P, int utt, int32_t* word_rows, int32_t
     if (!P || utt < 0 || utt >= P->n_utt) return fail(LA_ERR_ARG, "bad utterance index");
     const int T = P->t_off[utt + 1] - P->t_off[utt];
     const int L = P->l_off[utt + 1] - P->l_off[utt];
-    const bool skew = bucket_for_pairs(L + 1) == 0;
+    const bool skew = bucket_for_pairs(L + 1) < kWaveBuckets;
     const int k2 = skew && L + 1 > 32;
     if (word_rows) *word_rows = skew ? (T + 31 + 7) / 8 : (T + 7) / 8;
     if (col_shift) *col_shift = k2 ? 1 : 0;
@@ -402,7 +403,7 @@ static int viterbi_impl(const la_plan* P, void* d_ws, int32_t* d_first, int32_t*
         vp.chunk = la::viterbi_chunk_frames(P->row_max[b]);
         vp.first = d_first; vp.last_plus1 = d_last; vp.score = d_score; vp.status = d_status;
         vp.dp_dump = d_dp;
-        if (b == 0) LA_CUDA(la::launch_viterbi_skew(vp, static_cast<cudaStream_t>(stream)));
+        if (b < kWaveBuckets) LA_CUDA(la::launch_viterbi_wave(vp, P->warps_max[b], static_cast<cudaStream_t>(stream)));
         else LA_CUDA(la::launch_viterbi(vp, kShape[b].K, P->warps_max[b], static_cast<cudaStream_t>(stream)));
     }
     P->last_stream = static_cast<cudaStream_t>(stream);

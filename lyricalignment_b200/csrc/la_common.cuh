@@ -152,7 +152,7 @@ cudaError_t launch_head_gather(const HeadGatherParams& g, cudaStream_t stream);
 
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
 cudaError_t launch_viterbi(const VitParams& p, int K, int warps, cudaStream_t stream);
-cudaError_t launch_viterbi_skew(const VitParams& p, cudaStream_t stream);
+cudaError_t launch_viterbi_wave(const VitParams& p, int warps, cudaStream_t stream);
 int viterbi_chunk_frames(int row_floats_max);
 int set_error(int code, const char* msg);
 // set_error records la_last_error() and returns code

@@ -390,262 +390,7 @@ __global__ void __launch_bounds__(MAXT) viterbi_kernel(const VitParams p) {
     }
 }
 
-// =============================================================================================
-// The wavefront kernel: utterances of up to 63 pairs, one warp each (the whole 2 000-clip batch).
-//
-// In the row-synchronous mapping above the loop-carried chain of a frame is DADD -> SHFL -> compare ->
-// select -> DADD: the shuffle (and the masking of lane 0 behind it) is a third of it. Here lane i runs i frames
-// BEHIND lane 0 (at step tau it works on frame tau - i), so the value it needs from its left neighbour -- that
-// lane's label score of frame tau - i - 1 -- was final one whole step earlier: the shuffle is issued a step ahead
-// and leaves the chain, which is then compare -> select -> DADD. The price is 31 extra steps per utterance.
-// * Emission rows are staged unskewed, 4 x 32-row chunks by one bulk copy each (+ the first 7 rows of stage 0
-//   mirrored behind the last stage, so an 8-step block never wraps); lane i reads row (tau - i) at its own
-//   column: the lane stride is (K - row_floats), odd in units of the access size, so the loads are bank-conflict
-//   free. The blank column would be a 4..32-way conflict (row_floats is a multiple of 4): the warp compacts it
-//   into a ring of its own once per chunk.
-// * Rows -31..0 read as zeros and every state starts at the floor, so the steps a lane runs before its frame 1
-//   leave it at exactly -1e7 (= the reference's untouched dp row 0, utils/alignment.py:144-152); lane 0 holds the
-//   row-0 presets and never executes frame 0. Steps past frame T-1 compute garbage that flows only into later
-//   garbage (the dependency runs left to right and forward in time) and into nibbles the walker masks.
-// * K = 2 lanes own pairs 2i-1 and 2i (columns 2i, 2i+1 of the row: ONE aligned 8-byte load); pair -1 is a dummy
-//   pinned at -inf.
-// * Backpointers: word row r of column c holds STEPS 8r..8r+7 of its lane, i.e. frames 8r + n - skew(c).
-// =============================================================================================
-constexpr int kSkStages = 4, kSkChunk = 32, kSkRows = kSkStages * kSkChunk, kSkMirror = 7;
-
-template <int K, bool DUMP>
-__device__ __forceinline__ void skew_run(const VitParams& p, unsigned char* smem, int utt, int T, int l0, int L) {
-    constexpr int SH = (K == 1) ? 0 : 1;                  // column of pair i = i + SH
-    constexpr int LOGK = (K == 1) ? 0 : 1;
-    constexpr int R = kSkRows;
-    const int lane = threadIdx.x;
-    const int wrow = p.m.e_row[utt];
-    const float* E = p.E + p.m.e_off[utt];
-    const int pairs_pad = p.m.bp_pairs[utt];              // 32 K
-    uint32_t* bp = p.bp + p.m.bp_off[utt];
-
-    float* rows = reinterpret_cast<float*>(smem);                          // [R + 7][wrow]
-    float* bl = rows + (R + kSkMirror) * p.row_floats_max;                 // [R + 8] compact blank column
-    uint64_t* full = reinterpret_cast<uint64_t*>(bl + R + 8);              // [kSkStages]
-
-    if (lane == 0) {
-        for (int s = 0; s < kSkStages; ++s) mbar_init(&full[s], 1);
-        mbar_fence_init();
-    }
-    // rows -32..-1 live in the last stage until chunk 3 replaces them
-    for (int i = lane; i < kSkChunk * wrow; i += 32) rows[(R - kSkChunk) * wrow + i] = 0.f;
-    bl[R - kSkChunk + lane] = 0.f;
-    __syncwarp();
-    const int nchunks = (T + kSkChunk - 1) / kSkChunk;
-    auto issue = [&](int c) {                             // lane 0: chunk c into stage c % 4 (+ the mirror rows)
-        const int st = c & (kSkStages - 1);
-        const int nr = min(kSkChunk, T - c * kSkChunk);
-        const uint32_t bytes = (uint32_t)nr * wrow * 4;
-        const uint32_t mbytes = st == 0 ? (uint32_t)min(kSkMirror, nr) * wrow * 4 : 0u;
-        const float* src = E + (int64_t)c * kSkChunk * wrow;
-        fence_proxy_async();
-        mbar_arrive_expect_tx(&full[st], bytes + mbytes);
-        bulk_g2s(rows + st * kSkChunk * wrow, src, bytes, &full[st]);
-        if (mbytes) bulk_g2s(rows + R * wrow, src, mbytes, &full[st]);
-    };
-    if (lane == 0)
-        for (int c = 0; c < min(kSkStages - 1, nchunks); ++c) issue(c);
-
-    // ---- per-lane constants ----------------------------------------------------------------
-    const int pair0 = K * lane - SH;
-    bool skip_ok[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        const int i = pair0 + j;
-        skip_ok[j] = (i >= 1 && i < L) ? (p.m.labels[l0 + i] != p.m.labels[l0 + i - 1]) : false;
-    }
-    const bool force0 = lane == 0;                        // K = 1: pair 0 has no left neighbour; K = 2: the dummy pair
-    // first emission column of the lane (pair i reads column 1 + i); lanes past the row read column 0
-    const int ecol = (K == 1) ? ((pair0 < L) ? 1 + pair0 : 0) : ((2 * lane + 1 < wrow) ? 2 * lane : 0);
-
-    mbar_wait(&full[0], 0);
-    const float e00 = rows[0], e01 = rows[1];
-    __syncwarp();
-    for (int i = lane; i < wrow; i += 32) { rows[i] = 0.f; rows[R * wrow + i] = 0.f; }   // row 0 (and its mirror) as zeros
-    __syncwarp();
-
-    double b[K], l[K];
-    uint32_t acc[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) { b[j] = kFloor; l[j] = kFloor; acc[j] = 0u; }
-    if (lane == 0) {                                      // row 0 presets (utils/alignment.py:151-152)
-        if (K == 1) { b[0] = (double)e00; l[0] = (double)e01; }
-        else { b[0] = -INFINITY; l[0] = -INFINITY; b[K - 1] = (double)e00; l[K - 1] = (double)e01; }
-    }
-    double q = kFloor;                                    // left neighbour's label score, one frame back
-
-    const int i_last = (L + SH) >> LOGK;                  // lane of pair L
-    const int nsteps = T + i_last;                        // steps 1 .. nsteps-1; lane i_last ends on frame T-1
-
-    // one pair-frame: the reference's comparisons (utils/alignment.py:78-117) with (q >= b && q >= l) folded into
-    // q >= max(b, l) -- identical for the finite / -inf values that occur
-#define LA_SKEW_CELL(J, EB, EL, SHIFT, ACC)                                               \
-    {                                                                                       \
-        const double bj = b[J], lj = l[J];                                                  \
-        const bool P_b = (J == 0) ? ((bj > qq) || force0) : (bj > qq);                      \
-        const bool P_l = lj > bj;                                                           \
-        const double alt = P_l ? lj : bj;                                                   \
-        const bool P_s = (qq >= alt) && skip_ok[J];                                         \
-        b[J] = (P_b ? bj : qq) + (EB);                                                      \
-        l[J] = (P_s ? qq : alt) + (EL);                                                     \
-        ACC |= ((P_b ? 0u : 1u) | (P_s ? 4u : (P_l ? 0u : 2u))) << (SHIFT);                 \
-        qq = lj;                                                                            \
-    }
-
-    // any single step (the first block, the tail, DUMP)
-    auto step = [&](int tau, const float* pe, const float* pb) {
-        const double qn = shfl_up_f64(l[K - 1], 1);
-        const double eb = (double)pb[0];
-        double qq = q;
-        const int sh4 = (tau & 7) * 4;
-#pragma unroll
-        for (int j = 0; j < K; ++j) LA_SKEW_CELL(j, eb, (double)pe[j], sh4, acc[j])
-        q = qn;
-        if (DUMP) {
-            const int t = tau - lane;
-            if (t >= 1 && t < T) {
-                double* drow = p.dp_dump + (int64_t)t * (2 * L + 1);
-#pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    const int pr = pair0 + j;
-                    if (pr >= 0 && pr <= L) drow[2 * pr] = b[j];
-                    if (pr >= 0 && pr < L) drow[2 * pr + 1] = l[j];
-                }
-            }
-        }
-        if ((tau & 7) == 7 || tau == nsteps - 1) {
-            uint32_t* w = bp + (int64_t)(tau >> 3) * pairs_pad + K * lane;
-            if (K == 2) *reinterpret_cast<uint2*>(w) = make_uint2(acc[0], acc[K - 1]);
-            else w[0] = acc[0];
-#pragma unroll
-            for (int j = 0; j < K; ++j) acc[j] = 0u;
-        }
-    };
-    // eight whole steps tau0 .. tau0+7 (tau0 a multiple of 8): emissions in registers up front, immediates everywhere
-    auto fast8 = [&](int tau0, const float* pe, const float* pb) {
-        float ebf[8], elf[8][K];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            ebf[i] = pb[i];
-            if (K == 2) {
-                const float2 v = *reinterpret_cast<const float2*>(pe + i * wrow);
-                elf[i][0] = v.x; elf[i][K - 1] = v.y;
-            } else {
-                elf[i][0] = pe[i * wrow];
-            }
-        }
-        uint32_t a[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) a[j] = 0u;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const double qn = shfl_up_f64(l[K - 1], 1);
-            const double eb = (double)ebf[i];
-            double qq = q;
-#pragma unroll
-            for (int j = 0; j < K; ++j) LA_SKEW_CELL(j, eb, (double)elf[i][j], 4 * i, a[j])
-            q = qn;
-        }
-        uint32_t* w = bp + (int64_t)(tau0 >> 3) * pairs_pad + K * lane;
-        if (K == 2) *reinterpret_cast<uint2*>(w) = make_uint2(a[0], a[K - 1]);
-        else w[0] = a[0];
-    };
-
-    const long long c_fwd0 = clock64();
-    int slot = (R - lane) & (R - 1);                      // staged row of frame tau0 - lane, tau0 = 0
-    for (int c = 0; c * kSkChunk < nsteps; ++c) {
-        if (c >= 1) {
-            __syncwarp();                                 // every lane is past chunk c-2
-            const int cn = c + kSkStages - 2;
-            if (lane == 0 && cn < nchunks) issue(cn);
-            if (c < nchunks) mbar_wait(&full[c & (kSkStages - 1)], (c / kSkStages) & 1);
-        }
-        if (c < nchunks) {                                // compact blank column of chunk c
-            const int r = (c & (kSkStages - 1)) * kSkChunk + lane;
-            bl[r] = rows[r * wrow];
-            if ((c & (kSkStages - 1)) == 0 && lane < kSkMirror) bl[R + lane] = rows[lane * wrow];
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int sb = 0; sb < 4; ++sb) {
-            const int tau0 = c * kSkChunk + sb * 8;
-            if (tau0 >= nsteps) break;
-            const float* pe = rows + slot * wrow + ecol;
-            const float* pb = bl + slot;
-            if (!DUMP && tau0 >= 8 && tau0 + 8 <= nsteps) {
-                fast8(tau0, pe, pb);
-            } else {
-                const int hi = min(tau0 + 8, nsteps);
-                for (int tau = max(tau0, 1); tau < hi; ++tau) step(tau, pe + (tau - tau0) * wrow, pb + (tau - tau0));
-            }
-            slot = (slot + 8) & (R - 1);
-        }
-    }
-#undef LA_SKEW_CELL
-
-    // ---- end-state pick (utils/alignment.py:157): S-1 iff dp[T-1][S-1] > dp[T-1][S-2]. Lane i_last stopped on
-    // frame T-1; pair L-1's label score of that frame is its own other slot or the q it would use next.
-    const int jL = (L + SH) & (K - 1);
-    const double f0 = (K == 2 && jL) ? b[K - 1] : b[0];
-    const double f1 = (K == 2 && jL) ? l[0] : q;
-    int k = (f0 > f1) ? 2 * L : 2 * L - 1;
-    double best = (f0 > f1) ? f0 : f1;
-    k = __shfl_sync(0xffffffffu, k, i_last);
-    best = __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(best), i_last),
-                            __shfl_sync(0xffffffffu, __double2loint(best), i_last));
-    __threadfence_block();
-    __syncwarp();                                          // the lanes' bp stores are ordered before the walker's loads
-    const long long c_fwd1 = clock64();
-    const int visited = backtrace_walk<LOGK, SH, true>(bp, pairs_pad, T, k, lane, p.first + l0, p.last_plus1 + l0);
-    if (lane == 0) {
-        p.status[utt] = (visited == L) ? 0 : 2;          // a missing label state -> ValueError upstream
-        p.score[utt] = best;
-        if (p.trace && blockIdx.x == 0) {
-            g_vit_trace[0] = (unsigned long long)(c_fwd0);
-            g_vit_trace[1] = (unsigned long long)(c_fwd1);
-            g_vit_trace[2] = (unsigned long long)clock64();
-            g_vit_trace[3] = (unsigned long long)T;
-        }
-    }
-}
-
-template <bool DUMP>
-__global__ void __launch_bounds__(32) viterbi_skew_kernel(const VitParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int utt = p.order[blockIdx.x];
-    const int T = p.m.t_off[utt + 1] - p.m.t_off[utt];
-    const int l0 = p.m.l_off[utt];
-    const int L = p.m.l_off[utt + 1] - l0;
-    if (L <= 0 || T <= 0) {
-        if (threadIdx.x == 0) {
-            p.status[utt] = (L <= 0) ? 1 : 2;
-            p.score[utt] = 0.0;
-        }
-        return;
-    }
-    if (L + 1 <= 32) skew_run<1, DUMP>(p, smem, utt, T, l0, L);
-    else skew_run<2, DUMP>(p, smem, utt, T, l0, L);
-}
-
-size_t viterbi_skew_smem_bytes(int row_floats_max) {
-    return (size_t)(kSkRows + kSkMirror) * row_floats_max * 4 + (kSkRows + 8) * 4 + kSkStages * 8 + 16;
-}
-
-cudaError_t launch_viterbi_skew(const VitParams& p_in, cudaStream_t stream) {
-    if (p_in.n_order <= 0) return cudaSuccess;
-    VitParams p = p_in;
-    static const int trace = [] { const char* e = getenv("LA_VIT_TRACE"); return e ? atoi(e) : 0; }();
-    p.trace = trace;
-    const size_t smem = viterbi_skew_smem_bytes(p.row_floats_max);
-    if (p.dp_dump) viterbi_skew_kernel<true><<<p.n_order, 32, smem, stream>>>(p);
-    else viterbi_skew_kernel<false><<<p.n_order, 32, smem, stream>>>(p);
-    return cudaGetLastError();
-}
+#include "la_viterbi_wave.cuh"
 
 // frames per chunk: a power of two (8-frame blocks and the hand-off ring index with masks), at most 32. The
 // per-chunk bookkeeping (barrier waits, refill) is worth ~700 cycles, so wide rows get the biggest chunk of which

@@ -284,6 +284,26 @@ def test_many_pairs_per_lane_buckets(L):
     assert int(res.status[0]) == 0
 
 
+@pytest.mark.parametrize("mode", [MODE_CTC, MODE_CE])
+def test_wave_kernel_shape_boundaries(mode):
+    """The wavefront kernel's launch shapes at their edges: 32 / 33 pairs (one -> two pairs per lane), 63 / 64 pairs
+    (one warp -> two), 255 / 257 pairs (4-warp -> 10-warp bucket), 639 / 640 pairs (last wave shape -> the
+    row-synchronous kernel), with T shorter than the pipeline is deep, T = 1, and T around the chunk sizes."""
+    rng = np.random.default_rng(77 + mode)
+    V = 733
+    specs = [(40, 31), (41, 32), (300, 62), (90, 63), (33, 64), (500, 254), (70, 255), (520, 256), (1300, 638),
+             (650, 639), (1, 1), (2, 1), (8, 3), (15, 7), (16, 8), (17, 8), (31, 12), (32, 12), (33, 12), (130, 100),
+             (65, 20), (79, 33), (81, 40), (1, 70), (200, 129)]
+    rows, t_len = [], []
+    for T, L in specs:
+        rows += _rand_rows(rng, 1, L, L, V - 2, p_rep=0.15)
+        t_len.append(T)
+    pred = (2.0 * rng.standard_normal((sum(t_len), V))).astype(np.float32)
+    pred[:, -1] = rng.uniform(-6, 6, size=pred.shape[0])
+    res, emis, codes = run_plan(pred, rows, mode, t_len)
+    check_against_oracle(pred, rows, mode, t_len, res, emis, codes, f"wave{mode}")
+
+
 def test_label_row_longer_than_limit_is_refused():
     from lyricalignment_b200._lib import LyricAlignError
     with pytest.raises(LyricAlignError):
