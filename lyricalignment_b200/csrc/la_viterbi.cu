@@ -70,10 +70,13 @@ __device__ __forceinline__ void ring_put(uint32_t addr, double v, uint32_t pred)
 }
 
 // ---- backtrace: one warp; a tile of 8 word rows (64 steps) x 8 columns of packed codes in registers ----------
-// The walker only ever moves to smaller t and smaller k, and an alignment advances about one pair per
-// tens of frames, so a tile anchored with the current column at its right edge usually lasts its full 64
-// frames; the NEXT tile (same 8 columns, the 8 word rows before) is requested as soon as the current one
-// is entered, which hides the ~700-cycle L2 round trip that a one-block look-ahead exposed on every block.
+// The walker only ever moves to smaller t and smaller k. A state is usually occupied for many frames, so the walk is
+// a search: "the latest frame <= t at which state k's code is non-zero". Every lane masks the two words it holds
+// (state type, steps behind the walker, frames <= 0), the four lanes that hold the walker's column vote, and the
+// walker jumps straight to the next transition anywhere in the tile's 64 steps: one iteration per transition or
+// per tile, not per 8-frame word (round 2's first version: 230 iterations for a 1500-frame clip, now ~75).
+// The NEXT tile (same 8 columns, the 8 word rows before) is requested as soon as the current one is entered, which
+// hides the L2 round trip in the time direction.
 // Layout: pair i lives in column i + SH. SKEW (the wavefront kernel): the lane that owns a column runs
 // s = (column >> LOGK) & 31 steps behind lane 0, and nibble n of word row r holds step 8r + n = frame + s.
 // Returns the number of label states visited (== L iff every label is on the path).
@@ -82,10 +85,11 @@ __device__ __forceinline__ int backtrace_walk(const uint32_t* __restrict__ bp, i
                                               int32_t* __restrict__ first, int32_t* __restrict__ lastp) {
     int visited = 0;
     if ((k & 1) && lane == 0) lastp[k >> 1] = T;
-    struct Tile { int b0, p0; uint32_t w0, w1; };         // rows [b0-7, b0], columns [p0, p0+7]; lane = (b0 - row) % 4 * 8 + col - p0
+    const int lr = lane >> 3, lc = lane & 7;              // this lane's word rows are b0 - lr and b0 - lr - 4, its column p0 + lc
+    struct Tile { int b0, p0; uint32_t w0, w1; };
     auto load_tile = [&](int b0, int p0) -> Tile {
-        const int pr = p0 + (lane & 7);
-        const int blk = b0 - (lane >> 3);
+        const int pr = p0 + lc;
+        const int blk = b0 - lr;
         const bool ok = pr >= 0 && pr < pairs_pad;
         Tile tl;
         tl.b0 = b0; tl.p0 = p0;
@@ -108,25 +112,37 @@ __device__ __forceinline__ int backtrace_walk(const uint32_t* __restrict__ bp, i
     while (t >= 1) {
         const int col = (k >> 1) + SH;
         const int s = skew_of(col);
-        const int tau = t + s, tb = tau >> 3;
-        if (!covers(cur, tb, col)) {
-            cur = covers(nxt, tb, col) ? nxt : load_tile(tb, col - 7);
+        const int tau = t + s;
+        if (!covers(cur, tau >> 3, col)) {
+            cur = covers(nxt, tau >> 3, col) ? nxt : load_tile(tau >> 3, col - 7);
             nxt = load_tile(cur.b0 - 8, col - 7);
         }
-        const int d = cur.b0 - tb;
-        const uint32_t word = __shfl_sync(0xffffffffu, d < 4 ? cur.w0 : cur.w1, (d & 3) * 8 + (col - cur.p0));
-        // codes of state k over this word: label states use bits 1-2 of each nibble, blank states bit 0
-        uint32_t m = (k & 1) ? (word & 0x66666666u) : (word & 0x11111111u);
-        m &= (0xffffffffu >> (28 - (tau & 7) * 4));        // steps above tau are already behind the walker
-        const int z = s - (tb << 3);                       // nibbles 0..z are frames <= 0: they carry no code
-        if (z >= 0) m &= (z >= 7) ? 0u : (0xffffffffu << ((z + 1) * 4));
-        if (m == 0u) {                                     // state k stays for the rest of the word
-            t = (tb << 3) - 1 - s;
+        // codes of state k in a word of row r: label states use bits 1-2 of each nibble, blank states bit 0; only steps
+        // <= tau (the rest is behind the walker) and > s (frames <= 0 carry no code)
+        const uint32_t kind = (k & 1) ? 0x66666666u : 0x11111111u;
+        const bool mine = lc == col - cur.p0;
+        auto masked = [&](uint32_t w, int r) -> uint32_t {
+            uint32_t m = w & kind;
+            const int hi = tau - 8 * r, lo = s + 1 - 8 * r;    // nibbles lo .. hi of this word are in range
+            if (hi < 7) m = hi < 0 ? 0u : (m & (0xffffffffu >> (28 - 4 * hi)));
+            if (lo > 0) m = lo > 7 ? 0u : (m & (0xffffffffu << (4 * lo)));
+            return mine ? m : 0u;
+        };
+        const int r0 = cur.b0 - lr;
+        const uint32_t m0 = masked(cur.w0, r0), m1 = masked(cur.w1, r0 - 4);
+        const uint32_t v0 = __ballot_sync(0xffffffffu, m0 != 0u), v1 = __ballot_sync(0xffffffffu, m1 != 0u);
+        if ((v0 | v1) == 0u) {                            // state k stays down to the bottom of the tile
+            t = ((cur.b0 - 7) << 3) - 1 - s;
             continue;
         }
-        const int ntau = (tb << 3) + ((31 - __clz(m)) >> 2);   // latest step <= tau with a non-zero code
-        t = ntau - s;
-        const uint32_t nib = (word >> ((ntau & 7) * 4)) & 0xFu;
+        // the lowest voting lane holds the highest row: that is the latest step
+        const int src = __ffs(v0 ? v0 : v1) - 1;
+        const uint32_t word = __shfl_sync(0xffffffffu, v0 ? cur.w0 : cur.w1, src);
+        const uint32_t m = __shfl_sync(0xffffffffu, v0 ? m0 : m1, src);
+        const int row = cur.b0 - (src >> 3) - (v0 ? 0 : 4);
+        const int nib_i = (31 - __clz(m)) >> 2;
+        t = (row << 3) + nib_i - s;                       // latest frame <= t with a non-zero code
+        const uint32_t nib = (word >> (nib_i * 4)) & 0xFu;
         const int code = (k & 1) ? (int)(nib >> 1) : (int)(nib & 1u);
         if (k & 1) {                                       // label state k occupied frames t..: onset
             if (lane == 0) first[k >> 1] = t;
