@@ -100,12 +100,10 @@ int la_plan_num_launches(const la_plan* plan);
  * code(blank state 2i) | code(label state 2i+1) << 1, code = k - backpointer in {0,1,2}. */
 int la_plan_utt_layout(const la_plan* plan, int utt, int64_t* emit_off_bytes, int32_t* row_floats,
                        int64_t* bp_off_bytes, int32_t* pairs_padded);
-/* introspection for tests, second half: how K3 lays utterance u's backpointers out. The packed table is
- * uint32 [word_rows][pairs_padded]; pair i lives in column i + col_shift. skew_log2k < 0: the row-synchronous
- * kernel, nibble t%8 of word row t/8 is frame t. skew_log2k >= 0: the wavefront kernel (utterances of up to 63
- * pairs) -- the lane that owns column c runs s = (c >> skew_log2k) & 31 frames behind lane 0, and nibble n of
- * word row r of column c is frame 8r + n - s (so word_rows = ceil((T_u + 31) / 8)). */
-int la_plan_utt_bp_layout(const la_plan* plan, int utt, int32_t* word_rows, int32_t* col_shift, int32_t* skew_log2k);
+/* introspection for tests, second half: the packed table is uint32 [word_rows = ceil(T_u/8)][pairs_padded]; nibble
+ * t%8 of word row t/8 is frame t; pair i lives in column i + col_shift (1 for utterances of 33..639 pairs, where a
+ * lane of the wavefront kernel owns the pairs 2j-1 and 2j; else 0). */
+int la_plan_utt_bp_layout(const la_plan* plan, int utt, int32_t* word_rows, int32_t* col_shift);
 
 /* ---- K2: fused log-softmax + label gather ----------------------------------------------
  * Replaces utils/alignment.py:123-134 (mode CTC) / :14-20 (mode CE): one streaming pass over

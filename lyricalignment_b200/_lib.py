@@ -28,8 +28,7 @@ SIGNATURES = {
     "la_plan_num_launches": (_c_int, [_vp]),
     "la_plan_utt_layout": (_c_int, [_vp, _c_int, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_int32),
                                     ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_int32)]),
-    "la_plan_utt_bp_layout": (_c_int, [_vp, _c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
-                                       ctypes.POINTER(ctypes.c_int32)]),
+    "la_plan_utt_bp_layout": (_c_int, [_vp, _c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "la_emit": (_c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "la_viterbi": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "la_viterbi_debug": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -422,16 +422,14 @@ def run_viterbi_core(dp_matrix, backtrace_dp_matrix, cur_log_prediction, cur_log
 def unpack_step_codes(plan: AlignPlan, ws: torch.Tensor, u: int) -> np.ndarray:
     """Expands utterance u's packed backpointers into codes[T][2L+1] (k - bt[t][k]; row 0 unused)."""
     eo, rf, bo, pp = plan.utt_layout(u)
-    nrow, shift, logk = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
-    _lib.check(_lib.load().la_plan_utt_bp_layout(plan.handle, u, ctypes.byref(nrow), ctypes.byref(shift),
-                                                 ctypes.byref(logk)), "la_plan_utt_bp_layout")
+    nrow, shift = ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(_lib.load().la_plan_utt_bp_layout(plan.handle, u, ctypes.byref(nrow), ctypes.byref(shift)),
+               "la_plan_utt_bp_layout")
     T, L = int(plan.t_len[u]), int(plan.l_len[u])
-    nblk = nrow.value
+    nblk, sh = nrow.value, shift.value
     words = ws[bo:bo + nblk * pp * 4].cpu().numpy().view(np.uint32).reshape(nblk, pp)
-    col = np.arange(L + 1) + shift.value                                    # column of pair i
-    skew = ((col >> logk.value) & 31) if logk.value >= 0 else np.zeros_like(col)
-    step = np.arange(T)[:, None] + skew[None, :]                            # [T][L+1]: where frame t of pair i sits
-    nib = (words[step // 8, col[None, :]] >> ((step % 8) * 4).astype(np.uint32)) & 0xF
+    t = np.arange(T)
+    nib = (words[t // 8][:, sh:sh + L + 1] >> ((t % 8) * 4)[:, None].astype(np.uint32)) & 0xF    # [T][L+1]
     codes = np.zeros((T, 2 * L + 1), np.int64)
     codes[:, 0::2] = nib & 1
     codes[:, 1::2] = (nib >> 1)[:, :L]

@@ -273,12 +273,12 @@ static int plan_create_impl(la_plan** out, int mode, int n_utt, int V, const int
         P->e_off[u] = (int64_t)e_floats;
         e_floats += (size_t)h_t_len[u] * P->e_row[u];
         P->bp_off[u] = (int64_t)bp_words;
-        if (bucket_of[u] < kWaveBuckets) {                         // wavefront kernel: word rows count STEPS (frames + up to 31)
+        if (bucket_of[u] < kWaveBuckets) {                         // wavefront kernel: pair i lives in column i + 1 from 33 pairs on
             const int pairs = h_l_len[u] + 1;
             const int warps = bucket_of[u] == 0 ? 1 : (pairs + 1 + 63) / 64;
             P->warps_max[bucket_of[u]] = std::max(P->warps_max[bucket_of[u]], warps);
             P->bp_pairs[u] = bucket_of[u] == 0 ? (pairs <= 32 ? 32 : 64) : 64 * warps;
-            bp_words += (size_t)((h_t_len[u] + 31 + 7) / 8) * P->bp_pairs[u];
+            bp_words += (size_t)((h_t_len[u] + 7) / 8) * P->bp_pairs[u];
         } else {
             const int warps = std::max(1, (h_l_len[u] + 1 + 32 * sh.K - 1) / (32 * sh.K));
             P->warps_max[bucket_of[u]] = std::max(P->warps_max[bucket_of[u]], warps);
@@ -358,15 +358,12 @@ int la_plan_utt_layout(const la_plan* P, int utt, int64_t* emit_off_bytes, int32
     return LA_OK;
 }
 
-int la_plan_utt_bp_layout(const la_plan* P, int utt, int32_t* word_rows, int32_t* col_shift, int32_t* skew_log2k) {
+int la_plan_utt_bp_layout(const la_plan* P, int utt, int32_t* word_rows, int32_t* col_shift) {
     if (!P || utt < 0 || utt >= P->n_utt) return fail(LA_ERR_ARG, "bad utterance index");
     const int T = P->t_off[utt + 1] - P->t_off[utt];
     const int L = P->l_off[utt + 1] - P->l_off[utt];
-    const bool skew = bucket_for_pairs(L + 1) < kWaveBuckets;
-    const int k2 = skew && L + 1 > 32;
-    if (word_rows) *word_rows = skew ? (T + 31 + 7) / 8 : (T + 7) / 8;
-    if (col_shift) *col_shift = k2 ? 1 : 0;
-    if (skew_log2k) *skew_log2k = skew ? k2 : -1;
+    if (word_rows) *word_rows = (T + 7) / 8;
+    if (col_shift) *col_shift = (bucket_for_pairs(L + 1) < kWaveBuckets && L + 1 > 32) ? 1 : 0;
     return LA_OK;
 }
 

@@ -69,89 +69,100 @@ __device__ __forceinline__ void ring_put(uint32_t addr, double v, uint32_t pred)
                  ::"r"(addr), "l"(__double_as_longlong(v)), "r"(pred));
 }
 
-// ---- backtrace: one warp; a tile of 8 word rows (64 steps) x 8 columns of packed codes in registers ----------
+// ---- backtrace: one warp; a tile of 32 word rows (256 frames) x 32 columns of packed codes in shared memory --------
 // The walker only ever moves to smaller t and smaller k. A state is usually occupied for many frames, so the walk is
-// a search: "the latest frame <= t at which state k's code is non-zero". Every lane masks the two words it holds
-// (state type, steps behind the walker, frames <= 0), the four lanes that hold the walker's column vote, and the
-// walker jumps straight to the next transition anywhere in the tile's 64 steps: one iteration per transition or
-// per tile, not per 8-frame word (round 2's first version: 230 iterations for a 1500-frame clip, now ~75).
-// The NEXT tile (same 8 columns, the 8 word rows before) is requested as soon as the current one is entered, which
-// hides the L2 round trip in the time direction.
-// Layout: pair i lives in column i + SH. SKEW (the wavefront kernel): the lane that owns a column runs
-// s = (column >> LOGK) & 31 steps behind lane 0, and nibble n of word row r holds step 8r + n = frame + s.
+// a search: "the latest frame <= t at which state k's code is non-zero". Lane r reads the word of tile row r in the
+// walker's column, masks it (state type, frames behind the walker, frame 0), the warp votes, and the walker jumps
+// straight to the next transition anywhere in the tile's 256 frames: one iteration per transition or per tile. A lone
+// warp issues a dependent instruction every ~5.5 cycles, so the iteration is written as the shortest chain that does
+// the job: every lane prepares its own candidate (frame << 2 | step) and ONE warp-wide max (REDUX) picks the latest;
+// the step is read off the position of the highest set bit (blank states:
+// bit 0 of a nibble = step 1; label states: bit 1 = step 1, bit 2 = step 2).
+// Tiles are fetched with 16-byte asynchronous copies; the NEXT tile (same columns, the 32 word rows before) is requested
+// as soon as the current one is entered, which hides the L2 round trip in the time direction. An utterance of up to 32
+// columns never leaves its tile sideways. Layout: pair i lives in column i + SH, nibble t%8 of word row t/8 is frame t.
+// `tiles`: 2 x kBtTileWords words of shared memory (16-byte aligned) the DP no longer needs.
 // Returns the number of label states visited (== L iff every label is on the path).
-template <int LOGK, int SH, bool SKEW>
+constexpr int kBtPitch = 36;                              // words per tile row: 32 columns + 4 (16-byte multiple, 4-way banks)
+constexpr int kBtTileWords = 32 * kBtPitch;
+constexpr size_t kBtSmemBytes = 2 * kBtTileWords * 4;
+
+template <int SH>
 __device__ __forceinline__ int backtrace_walk(const uint32_t* __restrict__ bp, int pairs_pad, int T, int k, int lane,
-                                              int32_t* __restrict__ first, int32_t* __restrict__ lastp) {
+                                              int32_t* __restrict__ first, int32_t* __restrict__ lastp, uint32_t* tiles) {
     int visited = 0;
     if ((k & 1) && lane == 0) lastp[k >> 1] = T;
-    const int lr = lane >> 3, lc = lane & 7;              // this lane's word rows are b0 - lr and b0 - lr - 4, its column p0 + lc
-    struct Tile { int b0, p0; uint32_t w0, w1; };
-    auto load_tile = [&](int b0, int p0) -> Tile {
-        const int pr = p0 + lc;
-        const int blk = b0 - lr;
-        const bool ok = pr >= 0 && pr < pairs_pad;
-        Tile tl;
-        tl.b0 = b0; tl.p0 = p0;
-        tl.w0 = (ok && blk >= 0) ? __ldcg(bp + (int64_t)blk * pairs_pad + pr) : 0u;
-        tl.w1 = (ok && blk >= 4) ? __ldcg(bp + (int64_t)(blk - 4) * pairs_pad + pr) : 0u;
-        return tl;
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    // tile `buf` <- word rows b0-31 .. b0 (row b0 first), columns p0 .. p0+31; one commit group
+    auto fetch = [&](int buf, int b0, int p0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int id = j * 32 + lane, rr = id >> 3, c4 = (id & 7) * 4;
+            const int row = b0 - rr;
+            const bool ok = row >= 0 && p0 + c4 < pairs_pad;
+            const uint32_t dst = tiles_u32 + (uint32_t)(buf * kBtTileWords + rr * kBtPitch + c4) * 4u;
+            const uint32_t* src = bp + (int64_t)(ok ? row : 0) * pairs_pad + (ok ? p0 + c4 : 0);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                         ::"r"(dst), "l"(src), "r"((uint32_t)ok) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto covers = [](const Tile& tl, int tb, int col) {
-        return (unsigned)(tl.b0 - tb) < 8u && (unsigned)(col - tl.p0) < 8u;
-    };
-    auto skew_of = [](int col) { return SKEW ? ((col >> LOGK) & 31) : 0; };
+    asm volatile("" : "+l"(first), "+l"(lastp));          // keep both pointers in registers (else: an LDC per iteration)
     int t = T - 1;
-    Tile cur, nxt;
-    {
-        const int col = (k >> 1) + SH;
-        const int tb = (t + skew_of(col)) >> 3;
-        cur = load_tile(tb, col - 7);
-        nxt = load_tile(tb - 8, col - 7);
-    }
+    int cur = 0, b0 = t >> 3, p0 = max(0, (((k >> 1) + SH) | 3) - 31);
+    __syncwarp();
+    fetch(0, b0, p0);
+    fetch(1, b0 - 32, p0);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    // per lane, per tile: first frame of this lane's word, its address inside the tile, and the nibbles that may hold a
+    // code at all (row 0: frame 0 carries none; rows < 0 were never fetched)
+    int base = (b0 - lane) << 3;
+    uint32_t live = base > 0 ? 0xffffffffu : (base == 0 ? 0xfffffff0u : 0u);
+    const uint32_t* trow = tiles + lane * kBtPitch - p0;
     while (t >= 1) {
         const int col = (k >> 1) + SH;
-        const int s = skew_of(col);
-        const int tau = t + s;
-        if (!covers(cur, tau >> 3, col)) {
-            cur = covers(nxt, tau >> 3, col) ? nxt : load_tile(tau >> 3, col - 7);
-            nxt = load_tile(cur.b0 - 8, col - 7);
+        if ((unsigned)(b0 - (t >> 3)) >= 32u || (unsigned)(col - p0) >= 32u) {
+            __syncwarp();                                 // every lane has read the tile that is about to be replaced
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if ((unsigned)(b0 - 32 - (t >> 3)) < 32u && (unsigned)(col - p0) < 32u) {   // the prefetched tile
+                b0 -= 32;
+                fetch(cur, b0 - 32, p0);
+                cur ^= 1;
+            } else {                                      // left the tile sideways (or jumped past a whole tile)
+                b0 = t >> 3;
+                p0 = max(0, (col | 3) - 31);
+                fetch(cur, b0, p0);
+                fetch(cur ^ 1, b0 - 32, p0);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            }
+            __syncwarp();
+            base = (b0 - lane) << 3;
+            live = base > 0 ? 0xffffffffu : (base == 0 ? 0xfffffff0u : 0u);
+            trow = tiles + cur * kBtTileWords + lane * kBtPitch - p0;
         }
-        // codes of state k in a word of row r: label states use bits 1-2 of each nibble, blank states bit 0; only steps
-        // <= tau (the rest is behind the walker) and > s (frames <= 0 carry no code)
-        const uint32_t kind = (k & 1) ? 0x66666666u : 0x11111111u;
-        const bool mine = lc == col - cur.p0;
-        auto masked = [&](uint32_t w, int r) -> uint32_t {
-            uint32_t m = w & kind;
-            const int hi = tau - 8 * r, lo = s + 1 - 8 * r;    // nibbles lo .. hi of this word are in range
-            if (hi < 7) m = hi < 0 ? 0u : (m & (0xffffffffu >> (28 - 4 * hi)));
-            if (lo > 0) m = lo > 7 ? 0u : (m & (0xffffffffu << (4 * lo)));
-            return mine ? m : 0u;
-        };
-        const int r0 = cur.b0 - lr;
-        const uint32_t m0 = masked(cur.w0, r0), m1 = masked(cur.w1, r0 - 4);
-        const uint32_t v0 = __ballot_sync(0xffffffffu, m0 != 0u), v1 = __ballot_sync(0xffffffffu, m1 != 0u);
-        if ((v0 | v1) == 0u) {                            // state k stays down to the bottom of the tile
-            t = ((cur.b0 - 7) << 3) - 1 - s;
+        // codes of state k in this lane's word, frames <= t only (the rest is behind the walker)
+        const uint32_t kind = ((k & 1) ? 0x66666666u : 0x11111111u) & live;
+        const int hi = t - base;                          // nibbles 0 .. hi are in range
+        const uint32_t upto = hi >= 7 ? 0xffffffffu : (hi < 0 ? 0u : (0xffffffffu >> (28 - 4 * hi)));
+        const uint32_t m = trow[col] & kind & upto;
+        const int pbit = 31 - __clz(m);                   // highest code bit of this lane's word (if any)
+        const uint32_t cand = m ? ((uint32_t)((base + (pbit >> 2)) << 2) | (uint32_t)((pbit & 3) ? (pbit & 3) : 1)) : 0u;
+        const uint32_t win = __reduce_max_sync(0xffffffffu, cand);   // one REDUX: the latest frame any lane found
+        if (win == 0u) {                                  // state k stays down to the bottom of the tile
+            t = ((b0 - 31) << 3) - 1;
             continue;
         }
-        // the lowest voting lane holds the highest row: that is the latest step
-        const int src = __ffs(v0 ? v0 : v1) - 1;
-        const uint32_t word = __shfl_sync(0xffffffffu, v0 ? cur.w0 : cur.w1, src);
-        const uint32_t m = __shfl_sync(0xffffffffu, v0 ? m0 : m1, src);
-        const int row = cur.b0 - (src >> 3) - (v0 ? 0 : 4);
-        const int nib_i = (31 - __clz(m)) >> 2;
-        t = (row << 3) + nib_i - s;                       // latest frame <= t with a non-zero code
-        const uint32_t nib = (word >> (nib_i * 4)) & 0xFu;
-        const int code = (k & 1) ? (int)(nib >> 1) : (int)(nib & 1u);
+        t = (int)(win >> 2);                              // latest frame <= t with a non-zero code
         if (k & 1) {                                       // label state k occupied frames t..: onset
             if (lane == 0) first[k >> 1] = t;
             ++visited;
         }
-        k -= code;
+        k -= (int)(win & 3u);
         if ((k & 1) && lane == 0) lastp[k >> 1] = t;       // new label state ends at frame t-1
         --t;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // nothing may still be writing shared memory at exit
     if (k & 1) {
         if (lane == 0) first[k >> 1] = 0;
         ++visited;
@@ -393,7 +404,8 @@ __global__ void __launch_bounds__(MAXT) viterbi_kernel(const VitParams p) {
     int k = (fin[0] > fin[1]) ? 2 * L : 2 * L - 1;
     const double best = (fin[0] > fin[1]) ? fin[0] : fin[1];
 
-    const int visited = backtrace_walk<0, 0, false>(bp, pairs_pad, T, k, lane, p.first + l0, p.last_plus1 + l0);
+    const int visited = backtrace_walk<0>(bp, pairs_pad, T, k, lane, p.first + l0, p.last_plus1 + l0,
+                                                    reinterpret_cast<uint32_t*>(smem));
     if (lane == 0) {
         p.status[utt] = (visited == L) ? 0 : 2;          // a missing label state -> ValueError upstream
         p.score[utt] = best;

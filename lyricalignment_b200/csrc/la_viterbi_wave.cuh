@@ -22,7 +22,7 @@
 //   later garbage (the dependency runs left to right and forward in time) and into nibbles the walker masks.
 // * K = 2 lanes own pairs 2i-1 and 2i (columns 2i, 2i+1 of the row: ONE aligned 8-byte load); pair -1 is a dummy
 //   pinned at -inf.
-// * Backpointers: word row r of column c holds STEPS 8r..8r+7 of its lane, i.e. frames 8r + n - skew(c).
+// * Backpointers leave the kernel un-skewed (one funnel shift per 8-step block): word row r holds frames 8r..8r+7.
 #pragma once
 // (included inside namespace la)
 
@@ -79,7 +79,7 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
     // ---- shared memory: per warp [R + 7 rows][pitch], blank ring [R + 8], S barriers; then progress words + hand-off rings
     const int pitch = MULTI ? kWvSlice : wrow;            // floats between staged rows
     const int pitch_alloc = MULTI ? kWvSlice : p.row_floats_max;
-    const size_t rows_bytes = (size_t)(R + kWvMirror) * pitch_alloc * 4;
+    const size_t rows_bytes = max((size_t)(R + kWvMirror) * pitch_alloc * 4, kBtSmemBytes);   // the walker reuses warp 0's
     const size_t warp_bytes = rows_bytes + (R + 8) * 4 + 64;
     float* rows = reinterpret_cast<float*>(smem + warp * warp_bytes);
     float* bl = reinterpret_cast<float*>(smem + warp * warp_bytes + rows_bytes);              // compact blank column, same slots
@@ -167,9 +167,9 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
     __syncwarp();                                         // this point follow generic READS and need no proxy fence)
 
     double b[K], l[K];
-    uint32_t acc[K];
+    uint32_t acc[K], prev[K];                             // codes of the current / the previous 8-step block
 #pragma unroll
-    for (int j = 0; j < K; ++j) { b[j] = kFloor; l[j] = kFloor; acc[j] = 0u; }
+    for (int j = 0; j < K; ++j) { b[j] = kFloor; l[j] = kFloor; acc[j] = 0u; prev[j] = 0u; }
     if (threadIdx.x == 0) {                               // row 0 presets (utils/alignment.py:151-152)
         if (K == 1) { b[0] = (double)e00; l[0] = (double)e01; }
         else { b[0] = -INFINITY; l[0] = -INFINITY; b[K - 1] = (double)e00; l[K - 1] = (double)e01; }
@@ -205,6 +205,30 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
     };
     auto hand_slot = [](int f) { return (uint32_t)(f & (kWvHand - 1)) * 8u; };
 
+    // Backpointers leave the kernel UN-skewed: word row r of a column holds frames 8r .. 8r+7. An 8-step block of lane
+    // i covers frames tau0 - i .. tau0 - i + 7, which straddle two such words unless i % 8 == 0: the word that the
+    // block completes is the top `o` nibbles of the previous block's codes followed by the bottom 8 - o of this one's
+    // (o = -i mod 8) -- one funnel shift -- and it belongs to row tau0/8 - ceil(i/8).
+    const int fs = 32 - 4 * ((-lane) & 7);
+    const int nrows = (T + 7) >> 3;
+    uint32_t* const bp_lane = bp + col0 - (int64_t)((lane + 7) >> 3) * pairs_pad;
+    auto emit = [&](int tau0, const uint32_t (&cur)[K]) {
+        const int row = (tau0 >> 3) - ((lane + 7) >> 3);
+        uint32_t w[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) { w[j] = __funnelshift_rc(prev[j], cur[j], fs); prev[j] = cur[j]; }
+        // a predicated store, not a branch: the rows differ between lanes, and a divergent branch here costs the
+        // lone warp ~150 cycles per block (reconvergence before the next shuffle)
+        const uint32_t ok = (unsigned)row < (unsigned)nrows;
+        uint32_t* dst = bp_lane + (int64_t)(tau0 >> 3) * pairs_pad;
+        if (K == 2)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.v2.b32 [%0], {%1, %2};\n\t}"
+                         ::"l"(dst), "r"(w[0]), "r"(w[K - 1]), "r"(ok) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.b32 [%0], %1;\n\t}"
+                         ::"l"(dst), "r"(w[0]), "r"(ok) : "memory");
+    };
+
     // any single step (the first block, the tail, DUMP)
     auto step = [&](int tau, const float* pe, const float* pb) {
         double qn = shfl_up_f64(l[K - 1], 1);
@@ -232,9 +256,7 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
             }
         }
         if ((tau & 7) == 7 || tau == nsteps - 1) {
-            uint32_t* w = bp + (int64_t)(tau >> 3) * pairs_pad + col0;
-            if (K == 2) *reinterpret_cast<uint2*>(w) = make_uint2(acc[0], acc[K - 1]);
-            else w[0] = acc[0];
+            emit(tau & ~7, acc);
 #pragma unroll
             for (int j = 0; j < K; ++j) acc[j] = 0u;
         }
@@ -273,9 +295,7 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
             if (kRight) put(put8 + 8u * i, l[K - 1]);
         }
         if (kRight && ((tau0 - 32) & (kWvHand - 1)) == kWvHand - 8) put(hand_put, l[K - 1]);   // frame tau0-24 -> slot 0
-        uint32_t* w = bp + (int64_t)(tau0 >> 3) * pairs_pad + col0;
-        if (K == 2) *reinterpret_cast<uint2*>(w) = make_uint2(a[0], a[K - 1]);
-        else w[0] = a[0];
+        emit(tau0, a);
     };
 
     const long long c_fwd0 = clock64();
@@ -324,6 +344,10 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
         if (slot >= R) slot -= R;
     }
 #undef LA_WAVE_CELL
+    {                                                     // the codes still waiting for the top of their word
+        const uint32_t zero[K] = {};
+        emit(((nsteps - 1) & ~7) + 8, zero);
+    }
 
     // ---- end-state pick (utils/alignment.py:157): S-1 iff dp[T-1][S-1] > dp[T-1][S-2]. Lane i_last of the last warp
     // stopped on frame T-1; pair L-1's label score of that frame is its own other slot or the q it would use next.
@@ -340,7 +364,8 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
     const long long c_fwd1 = clock64();
     const int k = (fin[0] > fin[1]) ? 2 * L : 2 * L - 1;
     const double best = (fin[0] > fin[1]) ? fin[0] : fin[1];
-    const int visited = backtrace_walk<LOGK, SH, true>(bp, pairs_pad, T, k, lane, p.first + l0, p.last_plus1 + l0);
+    const int visited = backtrace_walk<SH>(bp, pairs_pad, T, k, lane, p.first + l0, p.last_plus1 + l0,
+                                                       reinterpret_cast<uint32_t*>(rows));   // warp 0's stages: the DP is done with them
     if (lane == 0) {
         p.status[utt] = (visited == L) ? 0 : 2;          // a missing label state -> ValueError upstream
         p.score[utt] = best;
@@ -353,9 +378,11 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
     }
 }
 
-// lone-warp shapes: 4 stages of 32 rows (a chunk boundary costs ~200 cycles of a lone warp's time); multi-warp
-// shapes: 4 stages of 16 rows (18 KB per warp, ten warps fit)
-constexpr int kWv1C = 32, kWv1S = 4, kWvMC = 16, kWvMS = 4;
+// Stage shapes. A lone warp with the SM to itself: 4 stages of 32 rows (64 steps of look-ahead, a chunk boundary
+// every 32 steps). A batch (more utterances than two per SM): 4 stages of 16 rows -- 14 KB per CTA at 48-float rows
+// instead of 27 KB, so 16 instead of 8 one-warp CTAs share an SM and hide each other's latencies (measured on the
+// 2 000-clip batch: issue slots 54 % busy at 8 CTAs per SM). Multi-warp shapes: 4 stages of 16 rows (18 KB per warp).
+constexpr int kWv1C = 32, kWv1S = 4, kWvBC = 16, kWvBS = 4, kWvMC = 16, kWvMS = 4;
 
 template <bool MULTI, bool DUMP, int MAXT>
 __global__ void __launch_bounds__(MAXT) viterbi_wave_kernel(const VitParams p) {
@@ -372,14 +399,19 @@ __global__ void __launch_bounds__(MAXT) viterbi_wave_kernel(const VitParams p) {
         return;
     }
     if (MULTI) wave_run<2, kWvMC, kWvMS, true, DUMP>(p, smem, utt, T, l0, L);
-    else if (L + 1 <= 32) wave_run<1, kWv1C, kWv1S, false, DUMP>(p, smem, utt, T, l0, L);
-    else wave_run<2, kWv1C, kWv1S, false, DUMP>(p, smem, utt, T, l0, L);
+    else if (p.chunk == kWvBC) {
+        if (L + 1 <= 32) wave_run<1, kWvBC, kWvBS, false, DUMP>(p, smem, utt, T, l0, L);
+        else wave_run<2, kWvBC, kWvBS, false, DUMP>(p, smem, utt, T, l0, L);
+    } else {
+        if (L + 1 <= 32) wave_run<1, kWv1C, kWv1S, false, DUMP>(p, smem, utt, T, l0, L);
+        else wave_run<2, kWv1C, kWv1S, false, DUMP>(p, smem, utt, T, l0, L);
+    }
 }
 
-static size_t viterbi_wave_smem_bytes(int row_floats_max, int warps) {
+static size_t viterbi_wave_smem_bytes(int row_floats_max, int warps, int chunk) {
     const bool multi = warps > 1;
-    const int R = multi ? kWvMC * kWvMS : kWv1C * kWv1S;
-    const size_t warp_bytes = (size_t)(R + kWvMirror) * (multi ? kWvSlice : row_floats_max) * 4 + (R + 8) * 4 + 64;
+    const int R = multi ? kWvMC * kWvMS : (chunk == kWvBC ? kWvBC * kWvBS : kWv1C * kWv1S);
+    const size_t warp_bytes = std::max((size_t)(R + kWvMirror) * (multi ? kWvSlice : row_floats_max) * 4, kBtSmemBytes) + (R + 8) * 4 + 64;
     return warps * warp_bytes + 128 + (multi ? (size_t)warps * (kWvHand + 8) * 8 : 0);
 }
 
@@ -407,7 +439,11 @@ cudaError_t launch_viterbi_wave(const VitParams& p_in, int warps, cudaStream_t s
     VitParams p = p_in;
     static const int trace = [] { const char* e = getenv("LA_VIT_TRACE"); return e ? atoi(e) : 0; }();
     p.trace = trace;
-    const size_t smem = viterbi_wave_smem_bytes(p.row_floats_max, warps);
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    static const int force = [] { const char* e = getenv("LA_WAVE_CHUNK"); return e ? atoi(e) : 0; }();   // A/B knob
+    p.chunk = force ? force : (p.n_order > 2 * sms ? kWvBC : kWv1C);
+    const size_t smem = viterbi_wave_smem_bytes(p.row_floats_max, warps, p.chunk);
     if (warps == 1) return launch_wave<false, 32>(p, 32, smem, stream);
     return launch_wave<true, 320>(p, 32 * warps, smem, stream);
 }
