@@ -79,7 +79,7 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
     // ---- shared memory: per warp [R + 7 rows][pitch], blank ring [R + 8], S barriers; then progress words + hand-off rings
     const int pitch = MULTI ? kWvSlice : wrow;            // floats between staged rows
     const int pitch_alloc = MULTI ? kWvSlice : p.row_floats_max;
-    const size_t rows_bytes = max((size_t)(R + kWvMirror) * pitch_alloc * 4, kBtSmemBytes);   // the walker reuses warp 0's
+    const size_t rows_bytes = max((size_t)(R + kWvMirror) * pitch_alloc * 4 + 256, kBtSmemBytes);   // the walker reuses warp 0's
     const size_t warp_bytes = rows_bytes + (R + 8) * 4 + 64;
     float* rows = reinterpret_cast<float*>(smem + warp * warp_bytes);
     float* bl = reinterpret_cast<float*>(smem + warp * warp_bytes + rows_bytes);              // compact blank column, same slots
@@ -146,8 +146,12 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
         skip_ok[j] = (i >= 1 && i < L) ? (p.m.labels[l0 + i] != p.m.labels[l0 + i - 1]) : false;
     }
     const bool force0 = threadIdx.x == 0;                 // K = 1: pair 0 has no left neighbour; K = 2: the dummy pair
-    // emission column of the lane inside its staged rows (pair i reads column 1 + i); lanes past the row read column 0
-    const int ecol = (K == 1) ? ((pair0 < L) ? 1 + pair0 : 0) : ((col0 + 1 < wrow) ? K * lane : 0);
+    // emission column of the lane inside its staged rows (pair i reads column 1 + i). Lanes past the utterance's last
+    // column keep the SAME address pattern and read whatever lies there (the next row, stale bytes: their pairs do not
+    // exist and feed nothing real): parking them all on column 0 put them on one bank -- a 32-way conflict on every load
+    // of the last warp of a wide utterance, which then set the pace of the whole pipeline (measured: 205 vs 153 cycles
+    // per step with 2 warps). The row area has 64 floats of slack for the overrun.
+    const int ecol = (K == 1) ? 1 + pair0 : K * lane;
     const bool has_left = MULTI && warp > 0, has_right = MULTI && warp < w_last;
     uint32_t lane0 = lane == 0, lane31 = lane == 31;
     const uint32_t prog_mine = smem_u32(prog + warp), prog_left = smem_u32(prog + max(warp, 1) - 1),
@@ -302,6 +306,7 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
     int slot = lane ? R - lane : 0;                       // staged row of frame tau0 - lane, tau0 = 0
     int st = 0, ph = 0;                                   // stage / parity of the chunk the current block starts
     int st_fill = AHEAD + 1;                              // stage that receives the next refill (that of chunk c - WIN - 1)
+    uint32_t seen_left = 0u, seen_right = 0u;             // neighbours' progress words as last read
     for (int sb = 0; sb * 8 < nsteps; ++sb) {
         const int tau0 = sb * 8;
         if (sb % SPB == 0 && sb) {                        // ---- chunk boundary: refill the stage that died, wait for chunk c
@@ -315,13 +320,14 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
             __syncwarp();
         }
         if (MULTI) {                                      // ---- flow control against the neighbours, once per block
+            // the last value seen is remembered: a neighbour that was already far enough costs no shared-memory round trip
             if (has_left) {
                 const uint32_t need = (uint32_t)min(tau0 + 8 + 31, T + 31);   // slots up to tau0 + 7 written
-                while (ld_progress(prog_left) < need) {}
+                while (seen_left < need) seen_left = ld_progress(prog_left);
             }
             if (has_right) {
                 const int need = tau0 - 23 - kWvHand;     // slots up to tau0 - 24 - kWvHand consumed
-                if (need > 0) while ((int)ld_progress(prog_right) < need) {}
+                while ((int)seen_right < need) seen_right = ld_progress(prog_right);
             }
         }
         const float* pe = rows + slot * pitch + ecol;
@@ -382,9 +388,10 @@ __device__ __forceinline__ void wave_run(const VitParams& p, unsigned char* smem
 // every 32 steps). A batch (more utterances than two per SM): 4 stages of 16 rows -- 14 KB per CTA at 48-float rows
 // instead of 27 KB, so 16 instead of 8 one-warp CTAs share an SM and hide each other's latencies (measured on the
 // 2 000-clip batch: issue slots 54 % busy at 8 CTAs per SM). Multi-warp shapes: 4 stages of 16 rows (18 KB per warp).
+// Up to four warps per CTA the multi-warp shapes use the lone warp's 4 x 32 rows (35 KB per warp).
 constexpr int kWv1C = 32, kWv1S = 4, kWvBC = 16, kWvBS = 4, kWvMC = 16, kWvMS = 4;
 
-template <bool MULTI, bool DUMP, int MAXT>
+template <bool MULTI, bool DUMP, int MAXT, int MC = kWvMC, int MS = kWvMS>
 __global__ void __launch_bounds__(MAXT) viterbi_wave_kernel(const VitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int utt = p.order[blockIdx.x];
@@ -398,7 +405,7 @@ __global__ void __launch_bounds__(MAXT) viterbi_wave_kernel(const VitParams p) {
         }
         return;
     }
-    if (MULTI) wave_run<2, kWvMC, kWvMS, true, DUMP>(p, smem, utt, T, l0, L);
+    if (MULTI) wave_run<2, MC, MS, true, DUMP>(p, smem, utt, T, l0, L);
     else if (p.chunk == kWvBC) {
         if (L + 1 <= 32) wave_run<1, kWvBC, kWvBS, false, DUMP>(p, smem, utt, T, l0, L);
         else wave_run<2, kWvBC, kWvBS, false, DUMP>(p, smem, utt, T, l0, L);
@@ -410,12 +417,12 @@ __global__ void __launch_bounds__(MAXT) viterbi_wave_kernel(const VitParams p) {
 
 static size_t viterbi_wave_smem_bytes(int row_floats_max, int warps, int chunk) {
     const bool multi = warps > 1;
-    const int R = multi ? kWvMC * kWvMS : (chunk == kWvBC ? kWvBC * kWvBS : kWv1C * kWv1S);
-    const size_t warp_bytes = std::max((size_t)(R + kWvMirror) * (multi ? kWvSlice : row_floats_max) * 4, kBtSmemBytes) + (R + 8) * 4 + 64;
+    const int R = multi ? (warps <= 4 ? kWv1C * kWv1S : kWvMC * kWvMS) : (chunk == kWvBC ? kWvBC * kWvBS : kWv1C * kWv1S);
+    const size_t warp_bytes = std::max((size_t)(R + kWvMirror) * (multi ? kWvSlice : row_floats_max) * 4 + 256, kBtSmemBytes) + (R + 8) * 4 + 64;
     return warps * warp_bytes + 128 + (multi ? (size_t)warps * (kWvHand + 8) * 8 : 0);
 }
 
-template <bool MULTI, int MAXT>
+template <bool MULTI, int MAXT, int MC = kWvMC, int MS = kWvMS>
 static cudaError_t launch_wave(const VitParams& p, int threads, size_t smem, cudaStream_t stream) {
     static bool attr_done[2][64] = {};
     int dev = 0;
@@ -423,13 +430,13 @@ static cudaError_t launch_wave(const VitParams& p, int threads, size_t smem, cud
     const int d = p.dp_dump ? 1 : 0;
     if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !attr_done[d][dev]) {
         cudaError_t e = p.dp_dump
-            ? cudaFuncSetAttribute(viterbi_wave_kernel<MULTI, true, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)
-            : cudaFuncSetAttribute(viterbi_wave_kernel<MULTI, false, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+            ? cudaFuncSetAttribute(viterbi_wave_kernel<MULTI, true, MAXT, MC, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)
+            : cudaFuncSetAttribute(viterbi_wave_kernel<MULTI, false, MAXT, MC, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e != cudaSuccess) return e;
         attr_done[d][dev] = true;
     }
-    if (p.dp_dump) viterbi_wave_kernel<MULTI, true, MAXT><<<p.n_order, threads, smem, stream>>>(p);
-    else viterbi_wave_kernel<MULTI, false, MAXT><<<p.n_order, threads, smem, stream>>>(p);
+    if (p.dp_dump) viterbi_wave_kernel<MULTI, true, MAXT, MC, MS><<<p.n_order, threads, smem, stream>>>(p);
+    else viterbi_wave_kernel<MULTI, false, MAXT, MC, MS><<<p.n_order, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -445,6 +452,7 @@ cudaError_t launch_viterbi_wave(const VitParams& p_in, int warps, cudaStream_t s
     p.chunk = force ? force : (p.n_order > 2 * sms ? kWvBC : kWv1C);
     const size_t smem = viterbi_wave_smem_bytes(p.row_floats_max, warps, p.chunk);
     if (warps == 1) return launch_wave<false, 32>(p, 32, smem, stream);
+    if (warps <= 4) return launch_wave<true, 128, kWv1C, kWv1S>(p, 32 * warps, smem, stream);
     return launch_wave<true, 320>(p, 32 * warps, smem, stream);
 }
 

@@ -1,5 +1,6 @@
 """K3 phase clocks (LA_VIT_TRACE=1): cycles spent in the DP and in the backtrace for a single 30 s clip (T=1500,
-L=40), a single-warp clip (T=600, L=24) and the long-form trellis (15000 x 600). Perf triage only."""
+L=40), a single-warp clip (T=600, L=24) and the long-form trellis (15000 x 600); more shapes: T:L pairs as arguments.
+Perf triage only."""
 import ctypes, os, sys
 os.environ["LA_VIT_TRACE"] = "1"
 import numpy as np, torch
@@ -10,7 +11,8 @@ lib.la_debug_viterbi_trace.argtypes = [ctypes.c_void_p]
 dev = torch.device("cuda", 0)
 rng = np.random.default_rng(0)
 V = 512
-for T, L in ((1500, 40), (600, 24), (15000, 600)):
+shapes = [tuple(int(x) for x in a.split(":")) for a in sys.argv[1:]] or [(1500, 40), (600, 24), (15000, 600)]
+for T, L in shapes:
     lab = rng.integers(2, 403, size=L).astype(np.int64)
     batch = synth.ClipBatch(np.array([T * 0.02]), np.array([T * 320]), np.array([T], np.int32), [lab])
     z = synth.planted_logits(batch, V, ctc=True, device=dev)
