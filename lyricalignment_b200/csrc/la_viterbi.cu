@@ -9,29 +9,23 @@
 // frame is computed (no pruning); unreachable cells start at the finite floor -1e7.
 //
 // Mapping: the 2L+1 states are grouped in L+1 "pairs" -- pair i = (blank state 2i, label state
-// 2i+1). A pair only needs ONE value from its left neighbour (the previous label's score), so a
-// thread that owns K consecutive pairs needs one 64-bit warp shuffle per frame. One CTA per
-// utterance with exactly ceil(pairs / 32K) warps. The dependency runs left to right only, so warps
-// are a PIPELINE, not a lock-step team: warp w hands the score of its last pair to warp w+1
-// through a shared-memory ring of 2 x chunk slots (a 64-bit store; the consumer's lane 0 spins on
-// an all-ones NaN sentinel and re-arms the slot). There is NO block barrier in the frame loop
-// (round 1's per-frame __syncthreads cost 160-250 ns per frame) and none per chunk either: the
-// emission stages are recycled through full/empty mbarriers, so the warps never re-align and the
-// pipeline never drains. A single warp is latency-bound on its own instruction stream (~5 cycles per
-// dependent instruction), so the common case -- one pair per lane, eight whole frames inside a chunk --
-// runs an unrolled block whose per-frame work is the dependent chain and nothing else.
-// Emission rows ([T][row_floats], col 0 = blank) are streamed in chunks of up to 32 frames into a
-// 3- or 4-deep shared-memory ring by 1-D TMA bulk copies issued by the last warp. Backpointers are
-// 2-bit step codes (k - bt), one nibble per pair per frame, 8 frames per 32-bit word, written coalesced.
-// Launch shapes (la_api.cu): one pair per lane up to 32 pairs, then TWO pairs per lane (a 41-pair clip is one
-// warp, not two: two independent chains per lane overlap their latencies, and half the warps means half the
-// instruction issue for a batch of clips), four / eight beyond 2048 / 4096 pairs.
-// The backtrace is a single warp walking t = T-1..1: lanes hold a 32-pair window of the current
-// 8-frame block in registers (next block prefetched); the walker takes the current pair's word by
-// shuffle and jumps straight to the next frame whose code is non-zero (count-leading-zeros on the
-// masked word), so its cost is one step per block plus one per transition, not one per frame.
-// Lane 0 emits first / last+1 at every label-state run boundary (the path is monotone, so each
-// label's occupancy is one run).
+// 2i+1). A pair only needs ONE value from its left neighbour (the previous label's score of the previous frame).
+// Two kernels share that mapping, the backpointer format and the backtrace:
+// * la_viterbi_wave.cuh -- the WAVEFRONT kernel, utterances of up to 639 pairs (every BASELINE config): lane i works
+//   i frames behind lane 0, so the neighbour's value is a step old when it is needed and the shuffle leaves the
+//   dependent chain. One warp up to 63 pairs, a pipeline of up to ten warps beyond. See that file.
+// * viterbi_kernel below -- the ROW-SYNCHRONOUS kernel, 640 .. 8192 pairs: all lanes work on the same frame, a thread
+//   owns K = 2/4/8 consecutive pairs and needs one 64-bit warp shuffle per frame; one CTA per utterance with exactly
+//   ceil(pairs / 32K) warps. The dependency runs left to right only, so warps are a PIPELINE, not a lock-step team:
+//   warp w hands the score of its last pair to warp w+1 through a shared-memory ring of 2 x chunk slots (a 64-bit
+//   store; the consumer polls an all-ones NaN sentinel and re-arms the slot). No block barrier in the frame loop and
+//   none per chunk either: the emission stages are recycled through full/empty mbarriers, so the warps never
+//   re-align and the pipeline never drains. Emission rows ([T][row_floats], col 0 = blank) are streamed in chunks of
+//   up to 32 frames into a 2- to 4-deep shared-memory ring by 1-D TMA bulk copies issued by the last warp.
+// Backpointers are 2-bit step codes (k - bt), one nibble per pair per frame, 8 frames per 32-bit word, written
+// coalesced. The backtrace (backtrace_walk) is a single warp searching shared-memory tiles of those words for the next
+// transition. Lane 0 emits first / last+1 at every label-state run boundary (the path is monotone, so each label's
+// occupancy is one run).
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>

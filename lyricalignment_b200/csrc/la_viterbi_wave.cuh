@@ -6,16 +6,18 @@
 // lane's label score of frame tau - i - 1 -- was final one whole step earlier: the shuffle is issued a step ahead
 // and leaves the chain, which is then compare -> select -> DADD. The price is 31 extra steps per warp.
 // * One warp up to 63 pairs (the whole 2 000-clip batch; one pair per lane up to 32 pairs, two from 33 on, chosen
-//   per utterance inside ONE launch); beyond that `W` warps of 64 columns each form a pipeline: warp w+1 runs >= 32
-//   steps behind warp w and takes the score of w's last pair from a shared-memory ring. No sentinels, no barrier:
-//   each warp publishes its step count (st.release) once per 8-step block, the consumer acquires it once per block,
-//   and a producer more than a ring ahead of its consumer waits the same way.
-// * Every warp stages ITS OWN columns of the emission rows: S stages of C rows by bulk copies (one per chunk for a
-//   lone warp -- whole rows are contiguous; one per row otherwise, each lane issuing one), plus the first 7 rows of
-//   stage 0 mirrored behind the last stage so an 8-step block never wraps. Lane i reads row (tau - i) at its own
-//   column: the lane stride is (K - pitch) floats, odd in units of the access size, so the loads are bank-conflict
-//   free. The blank column would be a 4..32-way conflict (the pitch is a multiple of 4): warp 0 compacts it into a
-//   ring every warp reads (the others are behind it by construction).
+//   per utterance inside ONE launch); beyond that `W` warps of 64 columns each form a pipeline: warp w+1 runs >= 40
+//   steps behind warp w and takes the score of w's last pair from a 64-slot shared-memory ring. No sentinels, no
+//   barrier, no fence: each warp publishes its step count (a volatile store by the lane that wrote the ring) once
+//   per 8-step block, the consumer re-reads it only when the value it remembers is not enough, and a producer more
+//   than a ring ahead of its consumer waits the same way.
+// * Every warp stages ITS OWN columns of the emission rows, S stages of C rows: a lone warp with ONE bulk copy (TMA)
+//   per chunk -- whole rows are contiguous; a warp of a wider utterance with 16-byte asynchronous copies (two
+//   256-byte row slices per instruction; per-lane bulk copies serialise into a ~12-instruction loop per row). The
+//   first 7 rows of stage 0 are mirrored behind the last stage so an 8-step block never wraps. Lane i reads row
+//   (tau - i) at its own column: the lane stride is (K - pitch) floats, odd in units of the access size, so the
+//   loads are bank-conflict free. The blank column would be a 4..32-way conflict (the pitch is a multiple of 4): it
+//   is fetched separately, 4 bytes per lane and row, into a compact ring with the same slots.
 // * Rows -31..0 read as zeros and every state starts at the floor, so the steps a lane runs before its frame 1
 //   leave it at exactly -1e7 (= the reference's untouched dp row 0, utils/alignment.py:144-152); lane 0 of warp 0
 //   holds the row-0 presets and never executes frame 0. Steps past frame T-1 compute garbage that flows only into

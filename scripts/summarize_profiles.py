@@ -54,7 +54,7 @@ def launches():
         f.write(f"# ncu launch list ({TAG}): `python bench.py --steps 2 --warmup 3 --skip-e2e --skip-head` under "
                 "`ncu --metrics gpu__time_duration.sum --clock-control none`\n\n"
                 "Per-launch times are cold-cache and serialised: compare SHARES, not absolutes. Filtered to the\n"
-                "product's kernels (`-k regex:emit_kernel|viterbi_kernel|logmel...`): 5 steps (3 warm-up + 2 timed) of the\n"
+                "product's kernels (`-k regex:emit_kernel|viterbi_|logmel...`): 5 steps (3 warm-up + 2 timed) of the\n"
                 "2000-clip workload; nothing else runs inside a step at N=1.\n\n"
                 "| kernel | launches | total us | mean us | share of all | share of la:: kernels |\n|---|---|---|---|---|---|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
@@ -68,7 +68,7 @@ def launches():
     print("launch list:", len(order), "launches")
 
 
-def full(name, pretty):
+def full(name, pretty, cmd=None):
     rep = os.path.join(SRC, f"{name}.ncu-rep")
     if not os.path.exists(rep):
         return None
@@ -77,9 +77,10 @@ def full(name, pretty):
     hdr, units = rows[0], rows[1]
     out = {}
     with open(os.path.join(OUT, f"{pretty}_{TAG}.md"), "w") as f:
-        f.write(f"# ncu --set full: {pretty} ({TAG})\n\nCommand: `ncu --set full --clock-control none --import-source on -k regex:{name} -s 3 -c 2 "
+        f.write(f"# ncu --set full: {pretty} ({TAG})\n\nCommand: " + (cmd or (
+                f"`ncu --set full --clock-control none --import-source on -k regex:{name} -s 3 -c 2 "
                 "python bench.py --clips 400 --steps 2 --warmup 3 --skip-e2e --skip-head` (400 clips keep the 40 replay passes short; "
-                "N1: `python scripts/bench_head.py 400`).\n\n")
+                "N1: `python scripts/bench_head.py 400`).")) + "\n\n")
         for li, vals in enumerate(rows[2:]):
             d = dict(zip(hdr, vals))
             f.write(f"## launch {li}: `{d.get('Kernel Name','')[:100]}` grid {d.get('launch__grid_size','?')} block {d.get('launch__block_size','?')}\n\n| metric | value | unit |\n|---|---|---|\n")
@@ -103,7 +104,11 @@ if __name__ == "__main__":
     launches()
     k2 = full("emit_kernel", "k2_emit")
     full("logmel_kernel", "k1_logmel")
-    full("viterbi_kernel", "k3_viterbi")
+    full("viterbi_wave_kernel", "k3_viterbi")
+    full("k3_wave_batch", "k3_viterbi_batch2000",
+         "`ncu --set full --warp-sampling-interval 0 --clock-control none --import-source on -k regex:viterbi_wave -s 2 -c 1 "
+         "python scripts/k3_single.py opencpop 2000 5`: K3 alone on the bench's 2 000-clip Opencpop-shaped batch (small V, the "
+         "emission rows are what K2 would have written).")
     full("head_lse_kernel", "n1_head_lse")
     if k2:
         rd = to_bytes(k2["dram__bytes_read.sum"], k2["_units"]["dram__bytes_read.sum"])
