@@ -14,7 +14,8 @@ One "step" = one pass of the WHOLE hot path over the batch, as SURVEY.md 8(d) de
  -> label flattening + la_plan_create (the replacement of the reference's per-utterance label strip and
     dp/bt allocation, utils/alignment.py:141-152) -- host work, INSIDE the timed region
  -> K2 fused log-softmax + gather over the head logits -> K3 Viterbi + backtrace
- -> D2H of first / last+1 / score / status -> numpy int32 on the host (and, at N > 1, the NCCL gather).
+ -> D2H of first / last+1 / score / status -> numpy int32 on the host.
+At N > 1 the K steps are followed by ONE NCCL gather of every step's alignments to rank 0, inside the timed region.
 
   value    : whole-job audio-s/s of that step; CUDA-event timed around the K steps, max over ranks.
   kernels  : the same three kernels timed alone (pre-built plan, nothing but launches), for reference.
@@ -229,8 +230,18 @@ def main():
         launches[0] = 3 + job.plan.num_launches        # K1: init + logmel + floor; K2; one K3 launch per bucket
         res = job.result()                              # first / last+1 int32, score, status: numpy on the host
         if world > 1:
-            sharded.gather_alignments(res, device=dev)  # NCCL: every rank's alignments to rank 0
+            pending.append(res)                         # gathered to rank 0 at the end of the job (final_gather)
         return res
+
+    pending = []
+
+    def final_gather():
+        """NCCL: every rank's alignments of every step to rank 0 -- the job's ONE exchange (north_star: 'NCCL only
+        for the final gather of alignments'), inside the timed region. Round 1 gathered inside every step, which
+        put all ranks in lock-step: each step then ran at the pace of that step's slowest rank."""
+        for r in pending:
+            sharded.gather_alignments(r, device=dev)
+        pending.clear()
 
     def note(msg):
         if rank == 0:
@@ -238,6 +249,7 @@ def main():
     note("inputs ready, warm-up")
     for _ in range(args.warmup):
         res = step()
+    final_gather()
     torch.cuda.synchronize()
     assert int(res.status.max()) == 0, "synthetic clips must all be feasible"
     l_len = res.l_len.astype(np.int64)
@@ -254,6 +266,7 @@ def main():
     t_start.record()
     for k in range(args.steps):
         step(ev[k])
+    final_gather()
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -272,6 +285,15 @@ def main():
         dist.all_reduce(audio_s, op=dist.ReduceOp.SUM)
     value = float(audio_s.item()) * args.steps / (ms_total / 1e3)
     step_ms = ms_total / args.steps
+    # per-rank diagnostics (outside the timed region): the job ends in a gather, so it runs at the pace of the slowest
+    # rank -- say which one that was and by how much (K1 start -> K2 end on each rank's own GPU, own wall of the loop)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([statistics.mean(e[0].elapsed_time(e[3]) for e in ev), t_start.elapsed_time(t_end) / args.steps],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"k1_to_k2_end_ms": [round(float(x[0]), 3) for x in allr], "step_ms": [round(float(x[1]), 3) for x in allr]}
 
     # ---- the three kernels alone (pre-built plan, launches only): explains `value`, is not `value` ----
     lens, cols = A._resolve_columns(A._flatten_labels(batch.labels), V - 2)
@@ -327,7 +349,7 @@ def main():
     # K3: 4 T (L+1) emissions read + ceil(S/4) T backpointer bytes written + read back + 8 L out.
     k3_bytes = emis_bytes + 2.0 * float(np.sum(tl64 * ((2 * l_len + 1 + 3) // 4))) + 8.0 * n_labels
     kernels = {"k1_logmel_ms": round(mel_ms, 4), "k2_emit_ms": round(emit_ms, 4),
-               "host_plan_k3_d2h_ms": round(step_ms - mel_ms - emit_ms, 4),
+               "host_plan_k3_d2h_ms": round(step_ms - mel_ms - emit_ms, 4), "per_rank": per_rank,
                "alone": {"k1_logmel_ms": round(k1_alone, 4), "k2_emit_ms": round(k2_alone, 4),
                          "k3_viterbi_ms": round(k3_alone, 4),
                          "sum_ms": round(k1_alone + k2_alone + k3_alone, 4),
@@ -547,10 +569,10 @@ def main():
             "config": {"workload": f"configs[1]: Opencpop-test-shaped batch, {args.clips} clips of 5-15 s per GPU, "
                                    f"V=21129 CTC decode, {n_labels} syllables, {total_T} frames",
                        "timed_region": "K1 -> label flattening + la_plan_create -> K2 -> K3 -> D2H -> int32 numpy on the host"
-                                       + (" -> NCCL gather to rank 0" if world > 1 else "") + " (public API: "
+                                       + (" (x steps) -> ONE NCCL gather of every step's alignments to rank 0, inside the timed region" if world > 1 else "") + " (public API: "
                                        "log_mel_spectrogram_ragged + align_clips_async().result())",
                        "l2_policy": f"inputs larger than L2 ({4.0 * total_T * V / 1e9:.1f} GB of logits resident in HBM per GPU)",
-                       "parallelism": f"utterance-sharded x{world}" + (", NCCL gather of alignments in the step" if world > 1 else "")},
+                       "parallelism": f"utterance-sharded x{world}" + (", one NCCL gather of all alignments at the end of the timed region" if world > 1 else "")},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "fused_head": head_leg,
             "gpu_launches": launches[0] * args.steps, "clocks": clk,
         }
