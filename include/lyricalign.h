@@ -116,7 +116,10 @@ int la_emit(const la_plan* plan, const float* d_logits, int64_t ld, const float*
 /* ---- K3: Viterbi DP + packed backpointers + backtrace ----------------------------------
  * Replaces run_viterbi_core (utils/alignment.py:73-119), the end-state pick and backtrace
  * (:157-176) and the on/offset scan (:182-185). fp64 state, reference tie order, finite
- * -1e7 floor; indices are bit-exact given identical emissions. */
+ * -1e7 floor; indices are bit-exact given identical emissions. One launch per non-empty size
+ * class of the plan: utterances of up to 63 / 255 / 639 state pairs (L + 1) run the lane-skewed
+ * wavefront kernel on 1 / up to 4 / up to 10 warps, longer ones (L <= LA_MAX_LABELS) the
+ * row-synchronous kernel; the packed backpointer table has the same layout either way. */
 int la_viterbi(const la_plan* plan, void* d_workspace, int32_t* d_first, int32_t* d_last_plus1,
                double* d_score, int32_t* d_status, void* stream);
 
